@@ -1,0 +1,707 @@
+// bev_pool for sm_100a: sorted-interval BEV pooling, forward / backward / precompute.
+//
+// Reference behaviour restated (not copied): mmdet3d/ops/bev_pool/src/bev_pool_cuda.cu:20-84
+// (one thread per (interval, channel), serial loop over the interval) and the Python glue in
+// mmdet3d/ops/bev_pool/bev_pool.py:38-98, mmdet3d/models/vtransforms/base.py:141-176.
+//
+// B200 design (HBM-bound, ~0.64 GB per launch at the C2 workload):
+//   * the sorted row stream is cut into CHUNK_ROWS-row chunks; one warp owns one chunk, so
+//     work per warp is uniform no matter how skewed the interval lengths are (1 .. >1000)
+//   * an interval belongs to the chunk that holds its first row and is reduced by that warp
+//     alone, except intervals longer than 2*CHUNK_ROWS which are cut at chunk boundaries into
+//     pieces; pieces land in a small partial buffer and a second tiny kernel adds them in
+//     fixed order -> results are bit-reproducible run to run (no float atomics)
+//   * rows are read with 16-byte streaming loads (ld.global.nc.L1::no_allocate.v4), G rows x
+//     C/4 quads = T*32 float4 per warp step, two steps in flight (>= 2*T*512 B per warp)
+//   * the per-lane partial sums are folded through shared memory once per interval and the
+//     finished row is stored with one coalesced 16-byte-per-lane store
+//   * `perm` variants read rows of the ORIGINAL feature tensor through the sorted->original
+//     map, which removes x[kept] / feats[indices] (2 x 0.6 GB of copies) from the frame
+#include <cub/device/device_radix_sort.cuh>
+
+#include "common.cuh"
+
+namespace bevb200 {
+
+constexpr int kChunkRows = 128;            // rows of the sorted stream owned by one warp
+constexpr int kLongRows = 2 * kChunkRows;  // intervals longer than this are cut into pieces
+constexpr int kPoolWarps = 8;              // warps per CTA
+
+struct PoolDims {
+  int b, d, h, w;
+};
+
+__device__ __forceinline__ long long cell_of(const int32_t *__restrict__ geom_feats, int row,
+                                             const PoolDims dm) {
+  // flat index into out[b][d][h][w] from (x, y, z, b) = geom_feats[row] (bev_pool_cuda.cu:34-36)
+  int4 g = *reinterpret_cast<const int4 *>(geom_feats + 4ll * row);
+  if ((unsigned)g.x >= (unsigned)dm.h || (unsigned)g.y >= (unsigned)dm.w ||
+      (unsigned)g.z >= (unsigned)dm.d || (unsigned)g.w >= (unsigned)dm.b)
+    return -1;
+  return (((long long)g.w * dm.d + g.z) * dm.h + g.x) * dm.w + g.y;
+}
+
+// last index i in [0, n) with starts[i] <= row, or -1
+__device__ __forceinline__ int find_interval(const int32_t *__restrict__ starts, int n, int row) {
+  int lo = 0, hi = n;  // first index with starts[i] > row
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (__ldg(starts + mid) <= row) lo = mid + 1; else hi = mid;
+  }
+  return lo - 1;
+}
+
+// ---------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------
+// Q = C/4 float4 per row, G rows per warp step, T = G*Q/32 float4 per lane per step.
+template <int Q, int G>
+struct PoolCfg {
+  static constexpr int T = G * Q / 32;
+  static_assert(G * Q % 32 == 0, "a warp step must be a whole number of float4 per lane");
+  static_assert(32 % G == 0, "G must divide the 32-row perm block");
+};
+
+template <int Q, int G>
+__device__ __forceinline__ void reduce_piece(const float4 *__restrict__ x,
+                                             const int32_t *__restrict__ perm, int s, int e,
+                                             float4 *__restrict__ dst, float4 *sm /*[G*Q]*/) {
+  constexpr int T = PoolCfg<Q, G>::T;
+  const int lane = lane_id();
+  int rig[T], qq[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    int f = lane + 32 * t;
+    rig[t] = f / Q;
+    qq[t] = f % Q;
+  }
+  float4 acc[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  for (int r0 = s; r0 < e; r0 += 32) {
+    // source rows of this 32-row block, one per lane
+    int row = r0 + lane;
+    int src = row < e ? (perm ? __ldg(perm + row) : row) : 0;
+    const int nrows = min(32, e - r0);
+#pragma unroll 1
+    for (int g0 = 0; g0 < nrows; g0 += 2 * G) {
+      float4 va[T], vb[T];
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        int ra = g0 + rig[t];
+        int sa = __shfl_sync(0xffffffffu, src, ra & 31);
+        va[t] = ra < nrows ? ldg_stream_f4(x + (long long)sa * Q + qq[t])
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (2 * G <= 32) {
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          int rb = g0 + G + rig[t];
+          int sb = __shfl_sync(0xffffffffu, src, rb & 31);
+          vb[t] = rb < nrows ? ldg_stream_f4(x + (long long)sb * Q + qq[t])
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        acc[t].x += va[t].x; acc[t].y += va[t].y; acc[t].z += va[t].z; acc[t].w += va[t].w;
+      }
+      if (2 * G <= 32) {
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          acc[t].x += vb[t].x; acc[t].y += vb[t].y; acc[t].z += vb[t].z; acc[t].w += vb[t].w;
+        }
+      }
+    }
+  }
+  // fold the G row-slots of every quad (fixed order) and store the finished row
+  __syncwarp();
+#pragma unroll
+  for (int t = 0; t < T; ++t) sm[lane + 32 * t] = acc[t];
+  __syncwarp();
+  for (int q = lane; q < Q; q += 32) {
+    float4 r = sm[q];
+#pragma unroll
+    for (int g = 1; g < G; ++g) {
+      float4 v = sm[g * Q + q];
+      r.x += v.x; r.y += v.y; r.z += v.z; r.w += v.w;
+    }
+    dst[q] = r;
+  }
+  __syncwarp();
+}
+
+template <int Q, int G>
+__global__ void __launch_bounds__(kPoolWarps * 32)
+    bevpool_fwd_kernel(const float4 *__restrict__ x, const int32_t *__restrict__ perm,
+                       const int32_t *__restrict__ geom_feats,
+                       const int32_t *__restrict__ starts, const int32_t *__restrict__ lengths,
+                       int n, int n_intervals, PoolDims dm, float4 *__restrict__ out,
+                       float4 *__restrict__ partial) {
+  __shared__ float4 sm_all[kPoolWarps][G * Q];
+  float4 *sm = sm_all[threadIdx.x >> 5];
+  const int nchunks = (n + kChunkRows - 1) / kChunkRows;
+  const int warps_total = gridDim.x * kPoolWarps;
+  for (int j = blockIdx.x * kPoolWarps + (threadIdx.x >> 5); j < nchunks; j += warps_total) {
+    const int c0 = j * kChunkRows, c1 = min(n, c0 + kChunkRows);
+    int i = find_interval(starts, n_intervals, c0);
+    // (a) a long interval that began before this chunk and reaches into it
+    if (i >= 0) {
+      int s = __ldg(starts + i), L = __ldg(lengths + i);
+      if (s < c0 && L > kLongRows && s + L > c0)
+        reduce_piece<Q, G>(x, perm, c0, min(s + L, c1), partial + (2ll * j) * Q, sm);
+      if (s < c0) ++i;
+    } else {
+      i = 0;
+    }
+    // (b) intervals whose first row lies in this chunk
+    for (; i < n_intervals; ++i) {
+      int s = __ldg(starts + i);
+      if (s >= c1) break;
+      int L = __ldg(lengths + i);
+      if (L <= 0) continue;
+      int e = min(s + L, n);
+      if (L > kLongRows) {
+        reduce_piece<Q, G>(x, perm, s, min(e, c1), partial + (2ll * j + 1) * Q, sm);
+      } else {
+        long long cell = cell_of(geom_feats, s, dm);
+        if (cell >= 0) reduce_piece<Q, G>(x, perm, s, e, out + cell * Q, sm);
+      }
+    }
+  }
+}
+
+// adds the pieces of every long interval in chunk order (one warp per interval)
+template <int Q>
+__global__ void __launch_bounds__(256)
+    bevpool_fwd_fixup_kernel(const int32_t *__restrict__ geom_feats,
+                             const int32_t *__restrict__ starts,
+                             const int32_t *__restrict__ lengths, int n, int n_intervals,
+                             PoolDims dm, float4 *__restrict__ out,
+                             const float4 *__restrict__ partial) {
+  const int lane = lane_id();
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n_intervals;
+       i += warps_total) {
+    int L = __ldg(lengths + i);
+    if (L <= kLongRows) continue;
+    int s = __ldg(starts + i);
+    int e = min(s + L, n);
+    long long cell = cell_of(geom_feats, s, dm);
+    if (cell < 0 || e <= s) continue;
+    int jf = s / kChunkRows, jl = (e - 1) / kChunkRows;
+    for (int q = lane; q < Q; q += 32) {
+      float4 r = partial[(2ll * jf + 1) * Q + q];
+      for (int j = jf + 1; j <= jl; ++j) {
+        float4 v = partial[(2ll * j) * Q + q];
+        r.x += v.x; r.y += v.y; r.z += v.z; r.w += v.w;
+      }
+      out[cell * Q + q] = r;
+    }
+  }
+}
+
+// any channel count: one thread per (interval, channel), like the reference kernel but on the
+// caller's stream and with bounds checks.  Used only when C is not one of the tuned widths.
+__global__ void bevpool_fwd_generic_kernel(const float *__restrict__ x,
+                                           const int32_t *__restrict__ perm,
+                                           const int32_t *__restrict__ geom_feats,
+                                           const int32_t *__restrict__ starts,
+                                           const int32_t *__restrict__ lengths, int n, int c,
+                                           int n_intervals, PoolDims dm, float *__restrict__ out) {
+  long long total = (long long)n_intervals * c;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int i = (int)(idx / c), ch = (int)(idx % c);
+    int s = starts[i], L = lengths[i];
+    if (L <= 0 || s < 0 || s >= n) continue;
+    int e = min(s + L, n);
+    long long cell = cell_of(geom_feats, s, dm);
+    if (cell < 0) continue;
+    float acc = 0.f;
+    for (int r = s; r < e; ++r) {
+      long long src = perm ? perm[r] : r;
+      acc += x[src * c + ch];
+    }
+    out[cell * c + ch] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// backward: x_grad[row, :] = out_grad[cell(interval(row)), :]
+// ---------------------------------------------------------------------------------------
+template <int Q, int G>
+__global__ void __launch_bounds__(kPoolWarps * 32)
+    bevpool_bwd_kernel(const float4 *__restrict__ out_grad, const int32_t *__restrict__ perm,
+                       const int32_t *__restrict__ geom_feats,
+                       const int32_t *__restrict__ starts, const int32_t *__restrict__ lengths,
+                       int n, int n_total, int n_intervals, PoolDims dm,
+                       float4 *__restrict__ x_grad) {
+  constexpr int T = PoolCfg<Q, G>::T;
+  const int lane = lane_id();
+  int rig[T], qq[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    int f = lane + 32 * t;
+    rig[t] = f / Q;
+    qq[t] = f % Q;
+  }
+  const int nchunks = (n_total + kChunkRows - 1) / kChunkRows;
+  const int warps_total = gridDim.x * kPoolWarps;
+  for (int j = blockIdx.x * kPoolWarps + (threadIdx.x >> 5); j < nchunks; j += warps_total) {
+    const int c0 = j * kChunkRows, c1 = min(n_total, c0 + kChunkRows);
+    int i = c0 < n ? find_interval(starts, n_intervals, c0) : n_intervals;
+    int r = c0;
+    while (r < c1) {
+      // next piece [r, pe): rows of interval i, or a gap of rows owned by no interval
+      // (filtered-out rows at the tail of perm, or holes between malformed intervals)
+      float4 g[T];
+      int pe;
+      bool have = false;
+      if (i >= 0 && i < n_intervals) {
+        int s = __ldg(starts + i), L = __ldg(lengths + i);
+        int e = min(s + max(L, 0), n);
+        if (r >= e) { ++i; continue; }
+        if (r >= s) {
+          pe = min(e, c1);
+          long long cell = cell_of(geom_feats, s, dm);
+          if (cell >= 0) {
+            have = true;
+#pragma unroll
+            for (int t = 0; t < T; ++t) g[t] = __ldg(out_grad + cell * Q + qq[t]);
+          }
+        } else {
+          pe = min(s, c1);
+        }
+      } else if (i < 0) {
+        int s0 = n_intervals > 0 ? __ldg(starts) : n_total;
+        pe = min(max(s0, r + 1), c1);
+        if (s0 <= r) { i = 0; continue; }
+      } else {
+        pe = c1;
+      }
+      if (!have) {
+#pragma unroll
+        for (int t = 0; t < T; ++t) g[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      for (int r0 = r; r0 < pe; r0 += 32) {
+        int row = r0 + lane;
+        int src = row < pe ? (perm ? __ldg(perm + row) : row) : 0;
+        const int nrows = min(32, pe - r0);
+        for (int g0 = 0; g0 < nrows; g0 += G) {
+#pragma unroll
+          for (int t = 0; t < T; ++t) {
+            int ra = g0 + rig[t];
+            int sa = __shfl_sync(0xffffffffu, src, ra & 31);
+            if (ra < nrows) stg_stream_f4(x_grad + (long long)sa * Q + qq[t], g[t]);
+          }
+        }
+      }
+      r = pe;
+    }
+  }
+}
+
+__global__ void bevpool_bwd_generic_kernel(const float *__restrict__ out_grad,
+                                           const int32_t *__restrict__ perm,
+                                           const int32_t *__restrict__ geom_feats,
+                                           const int32_t *__restrict__ starts,
+                                           const int32_t *__restrict__ lengths, int n, int c,
+                                           int n_intervals, PoolDims dm,
+                                           float *__restrict__ x_grad) {
+  long long total = (long long)n_intervals * c;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int i = (int)(idx / c), ch = (int)(idx % c);
+    int s = starts[i], L = lengths[i];
+    if (L <= 0 || s < 0 || s >= n) continue;
+    int e = min(s + L, n);
+    long long cell = cell_of(geom_feats, s, dm);
+    if (cell < 0) continue;
+    float g = out_grad[cell * c + ch];
+    for (int r = s; r < e; ++r) {
+      long long src = perm ? perm[r] : r;
+      x_grad[src * c + ch] = g;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host dispatch
+// ---------------------------------------------------------------------------------------
+static size_t pool_partial_bytes(int n, int c) {
+  size_t nchunks = ((size_t)n + kChunkRows - 1) / kChunkRows;
+  return align_up(2 * nchunks * (size_t)c * sizeof(float));
+}
+
+template <int Q, int G>
+static int launch_fwd(const float *x, const int32_t *perm, const int32_t *geom,
+                      const int32_t *starts, const int32_t *lengths, int n, int n_intervals,
+                      PoolDims dm, float *out, float *partial, cudaStream_t st) {
+  int nchunks = (n + kChunkRows - 1) / kChunkRows;
+  int grid = min((nchunks + kPoolWarps - 1) / kPoolWarps, kNumSMs * 4);
+  BEVB200_LAUNCH((bevpool_fwd_kernel<Q, G>), grid, kPoolWarps * 32, 0, st, (const float4 *)x, perm,
+                 geom, starts, lengths, n, n_intervals, dm, (float4 *)out, (float4 *)partial);
+  int fgrid = min((n_intervals + 7) / 8, kNumSMs * 4);
+  BEVB200_LAUNCH((bevpool_fwd_fixup_kernel<Q>), fgrid, 256, 0, st, geom, starts, lengths, n,
+                 n_intervals, dm, (float4 *)out, (const float4 *)partial);
+  return BEVB200_OK;
+}
+
+template <int Q, int G>
+static int launch_bwd(const float *og, const int32_t *perm, const int32_t *geom,
+                      const int32_t *starts, const int32_t *lengths, int n, int n_total,
+                      int n_intervals, PoolDims dm, float *xg, cudaStream_t st) {
+  int nchunks = (n_total + kChunkRows - 1) / kChunkRows;
+  int grid = min((nchunks + kPoolWarps - 1) / kPoolWarps, kNumSMs * 4);
+  BEVB200_LAUNCH((bevpool_bwd_kernel<Q, G>), grid, kPoolWarps * 32, 0, st, (const float4 *)og, perm,
+                 geom, starts, lengths, n, n_total, n_intervals, dm, (float4 *)xg);
+  return BEVB200_OK;
+}
+
+#define BEVB200_POOL_DISPATCH(C, CALL, FALLBACK) \
+  switch (C) {                                   \
+    case 16: CALL(4, 32); break;                 \
+    case 32: CALL(8, 16); break;                 \
+    case 64: CALL(16, 8); break;                 \
+    case 80: CALL(20, 8); break;                 \
+    case 96: CALL(24, 4); break;                 \
+    case 128: CALL(32, 4); break;                \
+    case 160: CALL(40, 4); break;                \
+    case 256: CALL(64, 2); break;                \
+    default: FALLBACK; break;                    \
+  }
+
+static int pool_forward(int b, int d, int h, int w, int n, int c, int n_intervals, const float *x,
+                        const int32_t *perm, const int32_t *geom, const int32_t *starts,
+                        const int32_t *lengths, float *out, void *ws, size_t ws_bytes,
+                        void *stream) {
+  BEVB200_REQUIRE(b > 0 && d > 0 && h > 0 && w > 0 && c > 0, "bad output shape");
+  BEVB200_REQUIRE(n >= 0 && n_intervals >= 0, "negative size");
+  BEVB200_REQUIRE(out != nullptr, "null out");
+  BEVB200_REQUIRE((long long)b * d * h * w * c < (1ll << 40), "output too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t out_bytes = (size_t)b * d * h * w * c * sizeof(float);
+  BEVB200_CUDA(cudaMemsetAsync(out, 0, out_bytes, st));
+  if (n == 0 || n_intervals == 0) return BEVB200_OK;
+  BEVB200_REQUIRE(x && geom && starts && lengths, "null input");
+  PoolDims dm{b, d, h, w};
+  int rc = BEVB200_OK;
+  bool aligned = ((uintptr_t)x % 16 == 0) && ((uintptr_t)out % 16 == 0);
+#define CALL_FWD(Q, G)                                                                         \
+  do {                                                                                         \
+    if (ws_bytes < pool_partial_bytes(n, c) || ws == nullptr) {                                \
+      snprintf(g_last_error, sizeof(g_last_error), "bev_pool: workspace too small (%zu < %zu)", \
+               ws_bytes, pool_partial_bytes(n, c));                                            \
+      return BEVB200_EWORKSPACE;                                                               \
+    }                                                                                          \
+    rc = launch_fwd<Q, G>(x, perm, geom, starts, lengths, n, n_intervals, dm, out, (float *)ws, st); \
+  } while (0)
+#define CALL_FWD_GENERIC()                                                                     \
+  do {                                                                                         \
+    BEVB200_LAUNCH(bevpool_fwd_generic_kernel, grid_for((long long)n_intervals * c, 256), 256, 0, \
+                   st, x, perm, geom, starts, lengths, n, c, n_intervals, dm, out);            \
+  } while (0)
+  if (!aligned) {
+    CALL_FWD_GENERIC();
+  } else {
+    BEVB200_POOL_DISPATCH(c, CALL_FWD, CALL_FWD_GENERIC());
+  }
+#undef CALL_FWD
+#undef CALL_FWD_GENERIC
+  return rc;
+}
+
+static int pool_backward(int b, int d, int h, int w, int n, int n_total, int c, int n_intervals,
+                         const float *og, const int32_t *perm, const int32_t *geom,
+                         const int32_t *starts, const int32_t *lengths, float *xg, void *stream) {
+  BEVB200_REQUIRE(b > 0 && d > 0 && h > 0 && w > 0 && c > 0, "bad grid shape");
+  BEVB200_REQUIRE(n >= 0 && n_total >= n && n_intervals >= 0, "bad sizes");
+  if (n_total == 0) return BEVB200_OK;
+  BEVB200_REQUIRE(xg != nullptr, "null x_grad");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0 || n_intervals == 0) {
+    BEVB200_CUDA(cudaMemsetAsync(xg, 0, (size_t)n_total * c * sizeof(float), st));
+    return BEVB200_OK;
+  }
+  BEVB200_REQUIRE(og && geom && starts && lengths, "null input");
+  PoolDims dm{b, d, h, w};
+  int rc = BEVB200_OK;
+  bool aligned = ((uintptr_t)og % 16 == 0) && ((uintptr_t)xg % 16 == 0);
+#define CALL_BWD(Q, G) \
+  rc = launch_bwd<Q, G>(og, perm, geom, starts, lengths, n, n_total, n_intervals, dm, xg, st)
+#define CALL_BWD_GENERIC()                                                                     \
+  do {                                                                                         \
+    BEVB200_CUDA(cudaMemsetAsync(xg, 0, (size_t)n_total * c * sizeof(float), st));             \
+    BEVB200_LAUNCH(bevpool_bwd_generic_kernel, grid_for((long long)n_intervals * c, 256), 256, 0, \
+                   st, og, perm, geom, starts, lengths, n, c, n_intervals, dm, xg);            \
+  } while (0)
+  if (!aligned) {
+    CALL_BWD_GENERIC();
+  } else {
+    BEVB200_POOL_DISPATCH(c, CALL_BWD, CALL_BWD_GENERIC());
+  }
+#undef CALL_BWD
+#undef CALL_BWD_GENERIC
+  return rc;
+}
+
+// ---------------------------------------------------------------------------------------
+// precompute: quantise / filter / rank / sort / interval table
+// ---------------------------------------------------------------------------------------
+struct QuantParams {
+  float lower[3], dx[3];
+  int nx[3];
+  int B, n_per_batch;
+};
+
+// keys[i] = rank of point i, or `dropped_key` (one past the largest rank) when filtered out
+__global__ void pool_rank_from_geom_kernel(const float *__restrict__ geom, int n, QuantParams p,
+                                           uint32_t dropped_key, uint32_t *__restrict__ keys,
+                                           uint32_t *__restrict__ vals) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    // base.py:149: ((geom - (bx - dx/2)) / dx).long()  -- fp32 sub, fp32 IEEE div, trunc to 0
+    long long idx[3];
+    bool kept = true;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      float v = __fdiv_rn(__fsub_rn(geom[3ll * i + k], p.lower[k]), p.dx[k]);
+      long long q = (long long)v;  // cvt.rzi.s64.f32 (NaN -> 0x8000.. : dropped below)
+      idx[k] = q;
+      kept = kept && q >= 0 && q < p.nx[k] && (v == v);
+    }
+    uint32_t key = dropped_key;
+    if (kept) {
+      int b = i / p.n_per_batch;
+      // bev_pool.py:87-92 with (B, D, H, W) = (B, nz, nx, ny): x*(W*D*B) + y*(D*B) + z*B + b
+      long long W = p.nx[1], D = p.nx[2], Bn = p.B;
+      key = (uint32_t)(idx[0] * (W * D * Bn) + idx[1] * (D * Bn) + idx[2] * Bn + b);
+    }
+    keys[i] = key;
+    vals[i] = (uint32_t)i;
+  }
+}
+
+__global__ void pool_rank_from_coords_kernel(const long long *__restrict__ coords, int n, int B,
+                                             int D, int H, int W, uint32_t dropped_key,
+                                             uint32_t *__restrict__ keys,
+                                             uint32_t *__restrict__ vals) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    long long cx = coords[4ll * i], cy = coords[4ll * i + 1], cz = coords[4ll * i + 2],
+              cb = coords[4ll * i + 3];
+    bool kept = cx >= 0 && cx < H && cy >= 0 && cy < W && cz >= 0 && cz < D && cb >= 0 && cb < B;
+    keys[i] = kept ? (uint32_t)(cx * ((long long)W * D * B) + cy * ((long long)D * B) + cz * B + cb)
+                   : dropped_key;
+    vals[i] = (uint32_t)i;
+  }
+}
+
+// after the sort: decode ranks into (x, y, z, b), flag interval heads
+__global__ void pool_heads_kernel(const uint32_t *__restrict__ keys_sorted, int n,
+                                  uint32_t dropped_key, int B, int D, int W,
+                                  int32_t *__restrict__ ranks_sorted,
+                                  int32_t *__restrict__ geom_sorted,
+                                  uint32_t *__restrict__ head_flags, int32_t *__restrict__ counts) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+    uint32_t key = keys_sorted[r];
+    bool kept = key < dropped_key;
+    uint32_t prev = r > 0 ? keys_sorted[r - 1] : 0xffffffffu;
+    head_flags[r] = (kept && (r == 0 || key != prev)) ? 1u : 0u;
+    ranks_sorted[r] = (int32_t)key;
+    int4 g = make_int4(0, 0, 0, 0);
+    if (kept) {
+      uint32_t rem = key;
+      g.w = rem % B; rem /= B;
+      g.z = rem % D; rem /= D;
+      g.y = rem % W; rem /= W;
+      g.x = rem;
+      uint32_t next = r + 1 < n ? keys_sorted[r + 1] : dropped_key;
+      if (next >= dropped_key) counts[0] = r + 1;  // n_kept (exactly one thread hits this)
+    }
+    *reinterpret_cast<int4 *>(geom_sorted + 4ll * r) = g;
+  }
+}
+
+__global__ void pool_starts_kernel(const uint32_t *__restrict__ head_flags,
+                                   const uint32_t *__restrict__ head_pos, int n,
+                                   int32_t *__restrict__ starts) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x)
+    if (head_flags[r]) starts[head_pos[r]] = r;
+}
+
+__global__ void pool_lengths_kernel(const int32_t *__restrict__ starts,
+                                    const int32_t *__restrict__ counts,
+                                    int32_t *__restrict__ lengths) {
+  const int n_kept = counts[0], n_int = counts[1];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_int; i += gridDim.x * blockDim.x)
+    lengths[i] = (i + 1 < n_int ? starts[i + 1] : n_kept) - starts[i];
+}
+
+struct PrepareWs {
+  uint32_t *keys_a, *keys_b, *vals_a, *flags, *pos, *tiles;
+  void *cub_tmp;
+  size_t cub_bytes;
+};
+
+static size_t prepare_layout(int n, void *ws, size_t ws_bytes, PrepareWs *out) {
+  Arena a(ws, ws_bytes);
+  PrepareWs w;
+  w.keys_a = a.take<uint32_t>(n);
+  w.keys_b = a.take<uint32_t>(n);
+  w.vals_a = a.take<uint32_t>(n);
+  w.flags = a.take<uint32_t>(n);
+  w.pos = a.take<uint32_t>(n);
+  w.tiles = a.take<uint32_t>(scan_scratch_elems(n));
+  size_t cub_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t *)nullptr,
+                                  (uint32_t *)nullptr, (const uint32_t *)nullptr,
+                                  (uint32_t *)nullptr, n > 0 ? n : 1, 0, 32, (cudaStream_t)0);
+  w.cub_bytes = cub_bytes;
+  w.cub_tmp = a.take<char>(cub_bytes);
+  if (out) *out = w;
+  return a.off;
+}
+
+static int prepare_finish(PrepareWs &w, int n, long long total_cells, int B, int D, int W,
+                          int32_t *ranks_sorted, int32_t *perm, int32_t *geom_sorted,
+                          int32_t *starts, int32_t *lengths, int32_t *counts, cudaStream_t st) {
+  int end_bit = 1;
+  while ((1ll << end_bit) <= total_cells && end_bit < 32) ++end_bit;  // keys in [0, total_cells]
+  size_t cub_bytes = w.cub_bytes;
+  // stable LSD radix sort: equal ranks keep ascending original index
+  BEVB200_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, cub_bytes, (const uint32_t *)w.keys_a,
+                                               w.keys_b, (const uint32_t *)w.vals_a,
+                                               (uint32_t *)perm, n, 0, end_bit, st));
+  g_launch_count += (end_bit + 7) / 8 + 2;  // cub: histogram + one onesweep pass per 8 bits
+  BEVB200_CUDA(cudaMemsetAsync(counts, 0, 2 * sizeof(int32_t), st));
+  BEVB200_LAUNCH(pool_heads_kernel, grid_for(n, 256), 256, 0, st, w.keys_b, n,
+                 (uint32_t)total_cells, B, D, W, ranks_sorted, geom_sorted, w.flags, counts);
+  int rc = exclusive_scan_u32(w.flags, w.pos, n, w.tiles, (uint32_t *)(counts + 1), false, st);
+  if (rc) return rc;
+  BEVB200_LAUNCH(pool_starts_kernel, grid_for(n, 256), 256, 0, st, w.flags, w.pos, n, starts);
+  BEVB200_LAUNCH(pool_lengths_kernel, grid_for(n, 256), 256, 0, st, starts, counts, lengths);
+  return BEVB200_OK;
+}
+
+}  // namespace bevb200
+
+using namespace bevb200;
+
+extern "C" {
+
+size_t bevb200_bev_pool_workspace_bytes(int n, int c) {
+  if (n < 0 || c <= 0) return 0;
+  return pool_partial_bytes(n, c);
+}
+
+int bevb200_bev_pool(int b, int d, int h, int w, int n, int c, int n_intervals, const float *x,
+                     const int32_t *geom_feats, const int32_t *interval_starts,
+                     const int32_t *interval_lengths, float *out, void *workspace,
+                     size_t workspace_bytes, void *stream) {
+  return pool_forward(b, d, h, w, n, c, n_intervals, x, nullptr, geom_feats, interval_starts,
+                      interval_lengths, out, workspace, workspace_bytes, stream);
+}
+
+int bevb200_bev_pool_perm(int b, int d, int h, int w, int n, int c, int n_intervals,
+                          const float *x, const int32_t *perm, const int32_t *geom_feats,
+                          const int32_t *interval_starts, const int32_t *interval_lengths,
+                          float *out, void *workspace, size_t workspace_bytes, void *stream) {
+  BEVB200_REQUIRE(perm != nullptr || n == 0, "null perm");
+  return pool_forward(b, d, h, w, n, c, n_intervals, x, perm, geom_feats, interval_starts,
+                      interval_lengths, out, workspace, workspace_bytes, stream);
+}
+
+int bevb200_bev_pool_grad(int b, int d, int h, int w, int n, int c, int n_intervals,
+                          const float *out_grad, const int32_t *geom_feats,
+                          const int32_t *interval_starts, const int32_t *interval_lengths,
+                          float *x_grad, void *stream) {
+  return pool_backward(b, d, h, w, n, n, c, n_intervals, out_grad, nullptr, geom_feats,
+                       interval_starts, interval_lengths, x_grad, stream);
+}
+
+int bevb200_bev_pool_grad_perm(int b, int d, int h, int w, int n, int n_total, int c,
+                               int n_intervals, const float *out_grad, const int32_t *perm,
+                               const int32_t *geom_feats, const int32_t *interval_starts,
+                               const int32_t *interval_lengths, float *x_grad, void *stream) {
+  BEVB200_REQUIRE(perm != nullptr || n_total == 0, "null perm");
+  return pool_backward(b, d, h, w, n, n_total, c, n_intervals, out_grad, perm, geom_feats,
+                       interval_starts, interval_lengths, x_grad, stream);
+}
+
+size_t bevb200_bev_pool_prepare_workspace_bytes(int n_total) {
+  if (n_total < 0) return 0;
+  return prepare_layout(n_total, nullptr, 0, nullptr);
+}
+
+int bevb200_bev_pool_prepare_geom(const float *geom_xyz, int n_total, int n_per_batch,
+                                  const float *lower_host, const float *dx_host,
+                                  const int32_t *nx_host, int B, int32_t *ranks_sorted,
+                                  int32_t *perm, int32_t *geom_sorted, int32_t *interval_starts,
+                                  int32_t *interval_lengths, int32_t *counts, void *workspace,
+                                  size_t workspace_bytes, void *stream) {
+  BEVB200_REQUIRE(n_total >= 0 && B > 0 && n_per_batch > 0, "bad sizes");
+  BEVB200_REQUIRE(lower_host && dx_host && nx_host && counts, "null argument");
+  BEVB200_REQUIRE((long long)n_per_batch * B >= n_total, "n_per_batch * B < n_total");
+  long long total_cells = (long long)nx_host[0] * nx_host[1] * nx_host[2] * B;
+  BEVB200_REQUIRE(nx_host[0] > 0 && nx_host[1] > 0 && nx_host[2] > 0, "bad grid");
+  BEVB200_REQUIRE(total_cells < 0xfffffff0ll, "grid too large for 32-bit ranks");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_total == 0) {
+    BEVB200_CUDA(cudaMemsetAsync(counts, 0, 2 * sizeof(int32_t), st));
+    return BEVB200_OK;
+  }
+  BEVB200_REQUIRE(geom_xyz && ranks_sorted && perm && geom_sorted && interval_starts &&
+                      interval_lengths, "null argument");
+  PrepareWs w;
+  size_t need = prepare_layout(n_total, workspace, workspace_bytes, &w);
+  if (workspace == nullptr || workspace_bytes < need) {
+    snprintf(g_last_error, sizeof(g_last_error), "bev_pool_prepare: workspace too small (%zu < %zu)",
+             workspace_bytes, need);
+    return BEVB200_EWORKSPACE;
+  }
+  QuantParams p;
+  for (int k = 0; k < 3; ++k) {
+    p.lower[k] = lower_host[k];
+    p.dx[k] = dx_host[k];
+    p.nx[k] = nx_host[k];
+  }
+  p.B = B;
+  p.n_per_batch = n_per_batch;
+  BEVB200_LAUNCH(pool_rank_from_geom_kernel, grid_for(n_total, 256), 256, 0, st, geom_xyz, n_total,
+                 p, (uint32_t)total_cells, w.keys_a, w.vals_a);
+  // (B, D, H, W) = (B, nz, nx, ny)
+  return prepare_finish(w, n_total, total_cells, B, nx_host[2], nx_host[1], ranks_sorted, perm,
+                        geom_sorted, interval_starts, interval_lengths, counts, st);
+}
+
+int bevb200_bev_pool_prepare_coords(const int64_t *coords, int n, int B, int D, int H, int W,
+                                    int32_t *ranks_sorted, int32_t *perm, int32_t *geom_sorted,
+                                    int32_t *interval_starts, int32_t *interval_lengths,
+                                    int32_t *counts, void *workspace, size_t workspace_bytes,
+                                    void *stream) {
+  BEVB200_REQUIRE(n >= 0 && B > 0 && D > 0 && H > 0 && W > 0, "bad sizes");
+  BEVB200_REQUIRE(counts != nullptr, "null counts");
+  long long total_cells = (long long)B * D * H * W;
+  BEVB200_REQUIRE(total_cells < 0xfffffff0ll, "grid too large for 32-bit ranks");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) {
+    BEVB200_CUDA(cudaMemsetAsync(counts, 0, 2 * sizeof(int32_t), st));
+    return BEVB200_OK;
+  }
+  BEVB200_REQUIRE(coords && ranks_sorted && perm && geom_sorted && interval_starts &&
+                      interval_lengths, "null argument");
+  PrepareWs w;
+  size_t need = prepare_layout(n, workspace, workspace_bytes, &w);
+  if (workspace == nullptr || workspace_bytes < need) {
+    snprintf(g_last_error, sizeof(g_last_error), "bev_pool_prepare: workspace too small (%zu < %zu)",
+             workspace_bytes, need);
+    return BEVB200_EWORKSPACE;
+  }
+  BEVB200_LAUNCH(pool_rank_from_coords_kernel, grid_for(n, 256), 256, 0, st,
+                 (const long long *)coords, n, B, D, H, W, (uint32_t)total_cells, w.keys_a, w.vals_a);
+  return prepare_finish(w, n, total_cells, B, D, W, ranks_sorted, perm, geom_sorted,
+                        interval_starts, interval_lengths, counts, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,129 @@
+"""SparseEncoder -- mirror of mmdet3d/models/backbones/sparse_encoder.py:11-217 (the VoxelNet
+middle encoder of BEVFusion's LiDAR branch), without mmcv / mmdet.  Same constructor, same
+sub-module names (conv_input, encoder_layers.encoder_layer{i}, conv_out) and state_dict."""
+import torch
+from torch import nn
+
+from . import spconv
+from .sparse_block import SparseBasicBlock, bn_scale_shift, make_sparse_convmodule
+from .spconv import ops as sp_ops
+
+
+class SparseEncoder(nn.Module):
+    def __init__(self, in_channels, sparse_shape, order=("conv", "norm", "act"),
+                 norm_cfg=dict(type="BN1d", eps=1e-3, momentum=0.01), base_channels=16,
+                 output_channels=128,
+                 encoder_channels=((16,), (32, 32, 32), (64, 64, 64), (64, 64, 64)),
+                 encoder_paddings=((1,), (1, 1, 1), (1, 1, 1), ((0, 1, 1), 1, 1)),
+                 block_type="conv_module"):
+        super().__init__()
+        assert block_type in ["conv_module", "basicblock"]
+        self.sparse_shape = sparse_shape
+        self.in_channels = in_channels
+        self.order = tuple(order)
+        self.base_channels = base_channels
+        self.output_channels = output_channels
+        self.encoder_channels = encoder_channels
+        self.encoder_paddings = encoder_paddings
+        self.stage_num = len(self.encoder_channels)
+        self.fp16_enabled = False
+        assert isinstance(order, (list, tuple)) and len(order) == 3
+        assert set(order) == {"conv", "norm", "act"}
+        if self.order[0] != "conv":  # pre activate
+            self.conv_input = make_sparse_convmodule(in_channels, self.base_channels, 3,
+                                                     norm_cfg=norm_cfg, padding=1,
+                                                     indice_key="subm1", conv_type="SubMConv3d",
+                                                     order=("conv",))
+        else:
+            self.conv_input = make_sparse_convmodule(in_channels, self.base_channels, 3,
+                                                     norm_cfg=norm_cfg, padding=1,
+                                                     indice_key="subm1", conv_type="SubMConv3d")
+        encoder_out_channels = self.make_encoder_layers(make_sparse_convmodule, norm_cfg,
+                                                        self.base_channels, block_type=block_type)
+        self.conv_out = make_sparse_convmodule(encoder_out_channels, self.output_channels,
+                                               kernel_size=(1, 1, 3), stride=(1, 1, 2),
+                                               norm_cfg=norm_cfg, padding=0,
+                                               indice_key="spconv_down2", conv_type="SparseConv3d")
+
+    def forward(self, voxel_features, coors, batch_size, fused=None, precision=None, **kwargs):
+        """sparse_encoder.py:99-132.  voxel_features [N, C] fp32, coors [N, 4] int32
+        (batch, x, y, z).  Returns spatial features [B, C*D, H, W].
+
+        fused=None picks the fused path (BN / ReLU / residual in the conv epilogues, dense()
+        written directly in the output layout) whenever the module is in eval mode."""
+        coors = coors.int()
+        if fused is None:
+            fused = not self.training and self.order == ("conv", "norm", "act")
+        x = spconv.SparseConvTensor(voxel_features, coors, self.sparse_shape, batch_size)
+        if fused:
+            return self._forward_fused(x, precision)
+        x = self.conv_input(x)
+        encode_features = []
+        for encoder_layer in self.encoder_layers:
+            x = encoder_layer(x)
+            encode_features.append(x)
+        out = self.conv_out(encode_features[-1])
+        spatial_features = out.dense()
+        N, C, H, W, D = spatial_features.shape
+        spatial_features = spatial_features.permute(0, 1, 4, 2, 3).contiguous()
+        return spatial_features.view(N, C * D, H, W)
+
+    @staticmethod
+    def _convmodule_fused(seq, x, precision):
+        conv, bn = seq[0], seq[1]
+        s, t = bn_scale_shift(bn)
+        return conv(x, scale=s, shift=t, relu=True, precision=precision)
+
+    def _forward_fused(self, x, precision):
+        x = self._convmodule_fused(self.conv_input, x, precision)
+        for stage in self.encoder_layers:
+            for block in stage:
+                if isinstance(block, SparseBasicBlock):
+                    x = block.forward_fused(x, precision)
+                else:
+                    x = self._convmodule_fused(block, x, precision)
+        out = self._convmodule_fused(self.conv_out, x, precision)
+        # dense() + permute(0,1,4,2,3) + view(N, C*D, H, W) in one kernel
+        return sp_ops.sparse_to_dense(out.features, out.indices, int(out.batch_size),
+                                      out.spatial_shape, z_major=True)
+
+    def make_encoder_layers(self, make_block, norm_cfg, in_channels, block_type="conv_module",
+                            conv_cfg=dict(type="SubMConv3d")):
+        """sparse_encoder.py:134-217."""
+        assert block_type in ["conv_module", "basicblock"]
+        self.encoder_layers = spconv.SparseSequential()
+        for i, blocks in enumerate(self.encoder_channels):
+            blocks_list = []
+            for j, out_channels in enumerate(tuple(blocks)):
+                padding = tuple(self.encoder_paddings[i])[j]
+                if i != 0 and j == 0 and block_type == "conv_module":
+                    blocks_list.append(make_block(in_channels, out_channels, 3, norm_cfg=norm_cfg,
+                                                  stride=2, padding=padding,
+                                                  indice_key=f"spconv{i + 1}",
+                                                  conv_type="SparseConv3d"))
+                elif block_type == "basicblock":
+                    if j == len(blocks) - 1 and i != len(self.encoder_channels) - 1:
+                        blocks_list.append(make_block(in_channels, out_channels, 3,
+                                                      norm_cfg=norm_cfg, stride=2, padding=padding,
+                                                      indice_key=f"spconv{i + 1}",
+                                                      conv_type="SparseConv3d"))
+                    else:
+                        blocks_list.append(SparseBasicBlock(out_channels, out_channels,
+                                                            norm_cfg=norm_cfg, conv_cfg=conv_cfg))
+                else:
+                    blocks_list.append(make_block(in_channels, out_channels, 3, norm_cfg=norm_cfg,
+                                                  padding=padding, indice_key=f"subm{i + 1}",
+                                                  conv_type="SubMConv3d"))
+                in_channels = out_channels
+            stage_name = f"encoder_layer{i + 1}"
+            self.encoder_layers.add_module(stage_name, spconv.SparseSequential(*blocks_list))
+        return out_channels
+
+
+def voxelnet_0p075_encoder():
+    """SparseEncoder as configured by configs/nuscenes/det/transfusion/secfpn/lidar/voxelnet_0p075.yaml."""
+    return SparseEncoder(in_channels=5, sparse_shape=[1440, 1440, 41], output_channels=128,
+                         order=("conv", "norm", "act"),
+                         encoder_channels=((16, 16, 32), (32, 32, 64), (64, 64, 128), (128, 128)),
+                         encoder_paddings=((0, 0, 1), (0, 0, 1), (0, 0, (1, 1, 0)), (0, 0)),
+                         block_type="basicblock")

@@ -1,0 +1,167 @@
+"""Sparse convolution modules -- mirror of mmdet3d/ops/spconv/conv.py:40-455.
+
+Same constructor arguments, parameter names and shapes (`weight [k0,k1,k2,Cin,Cout]`, optional
+`bias [Cout]`, conv.py:100-104) so reference state_dicts load unchanged.  The forward pass builds
+(or re-uses) a neighbour-table rulebook and runs ONE implicit-GEMM kernel per conv."""
+import math
+
+import numpy as np
+import torch
+from torch.nn import init
+from torch.nn.parameter import Parameter
+
+from . import functional as Fsp
+from . import ops
+from .modules import SparseModule
+from .structure import SparseConvTensor
+
+# registry used by make_sparse_convmodule / configs (the reference registers these names in
+# mmcv's CONV_LAYERS, conv.py:226-455)
+CONV_LAYERS = {}
+
+
+def register(cls):
+    CONV_LAYERS[cls.__name__] = cls
+    return cls
+
+
+def _calculate_fan_in_and_fan_out_hwio(tensor):
+    dimensions = tensor.ndimension()
+    if dimensions < 2:
+        raise ValueError("fan in and fan out can not be computed for tensor with fewer than 2 dimensions")
+    if dimensions == 2:
+        fan_in, fan_out = tensor.size(-2), tensor.size(-1)
+    else:
+        num_input_fmaps, num_output_fmaps = tensor.size(-2), tensor.size(-1)
+        receptive_field_size = 1
+        if tensor.dim() > 2:
+            receptive_field_size = tensor[..., 0, 0].numel()
+        fan_in = num_input_fmaps * receptive_field_size
+        fan_out = num_output_fmaps * receptive_field_size
+    return fan_in, fan_out
+
+
+class SparseConvolution(SparseModule):
+    def __init__(self, ndim, in_channels, out_channels, kernel_size=3, stride=1, padding=0,
+                 dilation=1, groups=1, bias=True, subm=False, output_padding=0, transposed=False,
+                 inverse=False, indice_key=None, fused_bn=False):
+        super().__init__()
+        assert groups == 1
+        if not isinstance(kernel_size, (list, tuple)):
+            kernel_size = [kernel_size] * ndim
+        if not isinstance(stride, (list, tuple)):
+            stride = [stride] * ndim
+        if not isinstance(padding, (list, tuple)):
+            padding = [padding] * ndim
+        if not isinstance(dilation, (list, tuple)):
+            dilation = [dilation] * ndim
+        if not isinstance(output_padding, (list, tuple)):
+            output_padding = [output_padding] * ndim
+        for d, s in zip(dilation, stride):
+            assert any([s == 1, d == 1]), "don't support this."
+        self.ndim = ndim
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.kernel_size = list(kernel_size)
+        self.conv1x1 = np.prod(kernel_size) == 1
+        self.stride = list(stride)
+        self.padding = list(padding)
+        self.dilation = list(dilation)
+        self.transposed = transposed
+        self.inverse = inverse
+        self.output_padding = list(output_padding)
+        self.groups = groups
+        self.subm = subm
+        self.indice_key = indice_key
+        self.fused_bn = fused_bn
+        self.weight = Parameter(torch.Tensor(*kernel_size, in_channels, out_channels))
+        if bias:
+            self.bias = Parameter(torch.Tensor(out_channels))
+        else:
+            self.register_parameter("bias", None)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        if self.bias is not None:
+            fan_in, _ = _calculate_fan_in_and_fan_out_hwio(self.weight)
+            bound = 1 / math.sqrt(fan_in)
+            init.uniform_(self.bias, -bound, bound)
+
+    # -- rulebook lookup / build (conv.py:152-182) ------------------------------------------
+    def _rulebook(self, input):
+        """Returns (Rulebook, out_spatial_shape).  Rulebooks are cached in input.indice_dict
+        under `indice_key` exactly like the reference, and additionally under a structural
+        key when indice_key is None: the rulebook is a pure function of (indices, geometry),
+        so SparseBasicBlock convs (which pass no key, sparse_block.py:62-110) share one
+        instead of rebuilding it per conv as the reference does."""
+        if self.transposed or self.inverse:
+            raise NotImplementedError("transposed / inverse sparse conv is outside the hot path")
+        indices = input.indices
+        key = self.indice_key
+        if key is None:
+            key = ("__auto__", indices.data_ptr(), indices.shape[0], tuple(input.spatial_shape),
+                   tuple(self.kernel_size), tuple(self.stride), tuple(self.padding),
+                   tuple(self.dilation), bool(self.subm))
+        datas = input.indice_dict.get(key, None)
+        if datas is not None:
+            outids, _, rb, _, out_shape = datas[0], datas[1], datas[2], datas[3], datas[5]
+            return rb, out_shape
+        rb, out_shape = ops.get_rulebook(indices, input.batch_size, input.spatial_shape,
+                                         self.kernel_size, self.stride, self.padding,
+                                         self.dilation, self.output_padding, self.subm,
+                                         self.transposed)
+        # (outids, indices, indice_pairs, indice_pair_num, spatial_shape) as conv.py:176-182,
+        # with the Rulebook object in the indice_pairs slot, plus the output shape
+        input.indice_dict[key] = (rb.outids, indices, rb, None, input.spatial_shape, out_shape)
+        return rb, out_shape
+
+    def forward(self, input, scale=None, shift=None, residual=None, relu=False, precision=None):
+        """conv.py:114-223.  The optional keyword arguments fuse eval-mode BatchNorm
+        (scale, shift), a residual add and ReLU into the conv epilogue."""
+        assert isinstance(input, SparseConvTensor)
+        features = input.features
+        if self.conv1x1:
+            features = torch.mm(input.features, self.weight.view(self.in_channels, self.out_channels))
+            if self.bias is not None:
+                features += self.bias
+            out_tensor = SparseConvTensor(features, input.indices, input.spatial_shape,
+                                          input.batch_size)
+            out_tensor.indice_dict = input.indice_dict
+            out_tensor.grid = input.grid
+            return out_tensor
+        rb, out_spatial_shape = self._rulebook(input)
+        fused = scale is not None or shift is not None or residual is not None or relu
+        if fused or not torch.is_grad_enabled() or not (features.requires_grad or self.weight.requires_grad):
+            if self.bias is not None:
+                # bias folds into the epilogue shift: (acc + b) * s + t = acc * s + (b * s + t)
+                b = self.bias.detach()
+                shift = b * scale + shift if scale is not None and shift is not None else (
+                    b * scale if scale is not None else (b + shift if shift is not None else b))
+            out_features = ops.sparse_conv(features.contiguous(), self.weight.detach().contiguous(),
+                                           rb.nbr, rb.n_out, scale, shift, residual, relu, precision)
+        else:
+            fn = Fsp.indice_subm_conv if self.subm else Fsp.indice_conv
+            out_features = fn(features, self.weight, rb, None, rb.n_out)
+            if self.bias is not None:
+                out_features += self.bias
+        out_tensor = SparseConvTensor(out_features, rb.outids, out_spatial_shape, input.batch_size)
+        out_tensor.indice_dict = input.indice_dict
+        out_tensor.grid = input.grid
+        return out_tensor
+
+
+@register
+class SparseConv3d(SparseConvolution):
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1,
+                 groups=1, bias=True, indice_key=None):
+        super().__init__(3, in_channels, out_channels, kernel_size, stride, padding, dilation,
+                         groups, bias, indice_key=indice_key)
+
+
+@register
+class SubMConv3d(SparseConvolution):
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1,
+                 groups=1, bias=True, indice_key=None):
+        super().__init__(3, in_channels, out_channels, kernel_size, stride, padding, dilation,
+                         groups, bias, True, indice_key=indice_key)

@@ -1,0 +1,249 @@
+"""spconv.ops -- host-side mirror of mmdet3d/ops/spconv/ops.py and of the pybind module
+`sparse_conv_ext` (src/all.cc:22-50), backed by libbevfusion_b200.so.
+
+Reference-compatible entry points (same names / argument order / return layouts):
+    get_conv_output_size, get_deconv_output_size
+    get_indice_pairs(...) -> (outids, indice_pairs[K,2,N], indice_pair_num[K])
+    indice_conv(features, filters, indice_pairs, indice_pair_num, num_activate_out, inverse, subm)
+    sparse_conv_ext.get_indice_pairs_3d / indice_conv_fp32
+B200-first entry points:
+    get_rulebook(...) -> Rulebook   (neighbour table nbr[K, n_out]; legacy pairs built lazily)
+    sparse_conv(features, weight, rulebook, scale, shift, residual, relu, precision)
+"""
+import ctypes
+import os
+
+import torch
+
+from .. import _C
+
+PREC_FP32, PREC_TF32X3, PREC_TF32 = 0, 1, 2
+_PREC_NAMES = {"fp32": PREC_FP32, "tf32x3": PREC_TF32X3, "tf32": PREC_TF32}
+
+
+def default_precision():
+    """Precision of the sparse-conv GEMMs: env BEVB200_SPCONV_PRECISION in {fp32, tf32x3, tf32}."""
+    return _PREC_NAMES[os.environ.get("BEVB200_SPCONV_PRECISION", "fp32").lower()]
+
+
+def get_conv_output_size(input_size, kernel_size, stride, padding, dilation):
+    # ops.py:20-31
+    ndim = len(input_size)
+    output_size = []
+    for i in range(ndim):
+        size = (input_size[i] + 2 * padding[i] - dilation[i] * (kernel_size[i] - 1) - 1) // stride[i] + 1
+        output_size.append(1 if kernel_size[i] == -1 else size)
+    return output_size
+
+
+def get_deconv_output_size(input_size, kernel_size, stride, padding, dilation, output_padding):
+    # ops.py:34-42
+    ndim = len(input_size)
+    output_size = []
+    for i in range(ndim):
+        if kernel_size[i] == -1:
+            raise ValueError("deconv don't support kernel_size < 0")
+        output_size.append((input_size[i] - 1) * stride[i] - 2 * padding[i] + kernel_size[i]
+                           + output_padding[i])
+    return output_size
+
+
+def _i32(vals):
+    return _C.host_array(ctypes.c_int32, [int(v) for v in vals])
+
+
+def _vp(arr):
+    return ctypes.cast(arr, ctypes.c_void_p)
+
+
+class Rulebook:
+    """Neighbour-table rulebook of one sparse conv: nbr[k, o] = input row or -1."""
+
+    def __init__(self, outids, nbr, n_in, n_out, kernel_volume):
+        self.outids, self.nbr = outids, nbr
+        self.n_in, self.n_out, self.kernel_volume = n_in, n_out, kernel_volume
+        self._pairs = None
+
+    def pairs(self):
+        """(indice_pairs [K, 2, n_in] int32 (-1 padded), indice_pair_num [K] int32): the
+        reference layout (spconv_ops.h:53-57)."""
+        if self._pairs is None:
+            dev = self.nbr.device
+            with torch.cuda.device(dev):
+                pairs = torch.empty((self.kernel_volume, 2, self.n_in), dtype=torch.int32, device=dev)
+                num = torch.empty((self.kernel_volume,), dtype=torch.int32, device=dev)
+                rc = _C.lib().bevb200_rulebook_to_pairs(_C.ptr(self.nbr), self.kernel_volume,
+                                                        self.n_out, self.n_in, _C.ptr(pairs),
+                                                        _C.ptr(num), _C.current_stream(dev))
+            _C.check(rc, "rulebook_to_pairs")
+            self._pairs = (pairs, num)
+        return self._pairs
+
+
+def _listify(v, ndim):
+    return list(v) if isinstance(v, (list, tuple)) else [v] * ndim
+
+
+def get_rulebook(indices, batch_size, spatial_shape, ksize=3, stride=1, padding=0, dilation=1,
+                 out_padding=0, subm=False, transpose=False):
+    """Build the rulebook of one conv on the device (replaces getIndicePair<3>,
+    spconv_ops.h:27-141).  One host sync for strided convs (the number of outputs)."""
+    _C.require_cuda(indices, "indices", torch.int32)
+    ndim = indices.shape[1] - 1
+    if ndim != 3:
+        raise NotImplementedError("only 3-D sparse convolution is implemented")
+    if transpose:
+        raise NotImplementedError("transposed sparse convolution is outside the hot path")
+    ksize, stride, padding = _listify(ksize, 3), _listify(stride, 3), _listify(padding, 3)
+    dilation = _listify(dilation, 3)
+    for d, s in zip(dilation, stride):
+        assert any([s == 1, d == 1]), "don't support this."
+    spatial_shape = [int(v) for v in spatial_shape]
+    if subm:
+        out_shape = spatial_shape
+    else:
+        out_shape = get_conv_output_size(spatial_shape, ksize, stride, padding, dilation)
+    batch_size = int(batch_size)
+    n_in = indices.shape[0]
+    kvol = ksize[0] * ksize[1] * ksize[2]
+    dev = indices.device
+    L = _C.lib()
+    hs, ho, hk, hst, hp, hd = (_i32(spatial_shape), _i32(out_shape), _i32(ksize), _i32(stride),
+                               _i32(padding), _i32(dilation))
+    with torch.cuda.device(dev):
+        stream = _C.current_stream(dev)
+        ws = torch.empty(max(L.bevb200_rulebook_workspace_bytes(n_in, batch_size, _vp(ho)), 256),
+                         dtype=torch.uint8, device=dev)
+        n_out_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        rc = L.bevb200_rulebook_prepare(_C.ptr(indices), n_in, batch_size, _vp(hs), _vp(ho), _vp(hk),
+                                        _vp(hst), _vp(hp), _vp(hd), int(bool(subm)),
+                                        _C.ptr(n_out_dev), _C.ptr(ws), ws.numel(), stream)
+        _C.check(rc, "rulebook_prepare")
+        if subm:
+            n_out, outids = n_in, indices
+        else:
+            n_out = int(n_out_dev.item())
+            outids = torch.empty((n_out, 4), dtype=torch.int32, device=dev)
+        nbr = torch.empty((kvol, n_out), dtype=torch.int32, device=dev)
+        rc = L.bevb200_rulebook_fill(_C.ptr(indices), n_in, batch_size, _vp(hs), _vp(ho), _vp(hk),
+                                     _vp(hst), _vp(hp), _vp(hd), int(bool(subm)), n_out,
+                                     _C.ptr(outids), _C.ptr(nbr), _C.ptr(ws), ws.numel(), stream)
+        _C.check(rc, "rulebook_fill")
+    return Rulebook(outids, nbr, n_in, n_out, kvol), out_shape
+
+
+def get_indice_pairs(indices, batch_size, spatial_shape, ksize=3, stride=1, padding=0, dilation=1,
+                     out_padding=0, subm=False, transpose=False, grid=None):
+    """Drop-in for ops.get_indice_pairs (ops.py:45-125): returns
+    (outids [M, 4], indice_pairs [K, 2, N], indice_pair_num [K])."""
+    rb, _ = get_rulebook(indices, batch_size, spatial_shape, ksize, stride, padding, dilation,
+                         out_padding, subm, transpose)
+    pairs, num = rb.pairs()
+    return rb.outids, pairs, num
+
+
+def nbr_from_pairs(indice_pairs, indice_pair_num, num_activate_out, inverse=False):
+    _C.require_cuda(indice_pairs, "indice_pairs", torch.int32)
+    _C.require_cuda(indice_pair_num, "indice_pair_num", torch.int32)
+    kvol, _, pdim = indice_pairs.shape
+    dev = indice_pairs.device
+    with torch.cuda.device(dev):
+        nbr = torch.empty((kvol, int(num_activate_out)), dtype=torch.int32, device=dev)
+        rc = _C.lib().bevb200_pairs_to_nbr(_C.ptr(indice_pairs), _C.ptr(indice_pair_num), kvol, pdim,
+                                           int(num_activate_out), int(bool(inverse)), _C.ptr(nbr),
+                                           _C.current_stream(dev))
+    _C.check(rc, "pairs_to_nbr")
+    return nbr
+
+
+def sparse_conv(features, weight, nbr, n_out, scale=None, shift=None, residual=None, relu=False,
+                precision=None):
+    """out[o] = epilogue(sum_k features[nbr[k, o]] @ weight[k]) -- one implicit-GEMM launch."""
+    _C.require_cuda(features, "features", torch.float32)
+    _C.require_cuda(weight, "weight", torch.float32)
+    _C.require_cuda(nbr, "nbr", torch.int32)
+    n_in, c_in = features.shape
+    c_out = weight.shape[-1]
+    kvol = nbr.shape[0]
+    assert weight.numel() == kvol * c_in * c_out, "weight must be [k..., Cin, Cout]"
+    assert nbr.shape[1] == n_out
+    for t, name in ((scale, "scale"), (shift, "shift")):
+        if t is not None:
+            _C.require_cuda(t, name, torch.float32)
+            assert t.numel() == c_out
+    if residual is not None:
+        _C.require_cuda(residual, "residual", torch.float32)
+        assert tuple(residual.shape) == (n_out, c_out)
+    if precision is None:
+        precision = default_precision()
+    dev = features.device
+    with torch.cuda.device(dev):
+        out = torch.empty((n_out, c_out), dtype=torch.float32, device=dev)
+        rc = _C.lib().bevb200_spconv_forward(
+            _C.ptr(features), _C.ptr(weight), _C.ptr(nbr), n_in, int(n_out), c_in, c_out, kvol,
+            _C.ptr(scale), _C.ptr(shift), _C.ptr(residual), int(bool(relu)), int(precision),
+            _C.ptr(out), _C.current_stream(dev))
+    _C.check(rc, "spconv_forward")
+    return out
+
+
+def indice_conv(features, filters, indice_pairs, indice_pair_num, num_activate_out, inverse=False,
+                subm=False, precision=None):
+    """Drop-in for ops.indice_conv (ops.py:128-152).  `indice_pairs` may be the reference
+    [K, 2, N] tensor (converted to a neighbour table first) or a Rulebook."""
+    if filters.dtype != torch.float32:
+        raise NotImplementedError("only fp32 filters are implemented (indice_conv_half: next)")
+    if isinstance(indice_pairs, Rulebook):
+        assert not inverse
+        nbr = indice_pairs.nbr
+    else:
+        nbr = nbr_from_pairs(indice_pairs, indice_pair_num, num_activate_out, inverse)
+    return sparse_conv(features.contiguous(), filters.contiguous(), nbr, int(num_activate_out),
+                       precision=precision)
+
+
+def indice_conv_backward(features, filters, out_bp, indice_pairs, indice_pair_num, inverse=False,
+                         subm=False):
+    raise NotImplementedError("sparse conv backward is not built yet (SURVEY.md section 8, a18)")
+
+
+class _SparseConvExt:
+    """Stand-in for the reference pybind module `sparse_conv_ext` (src/all.cc)."""
+
+    @staticmethod
+    def get_indice_pairs_3d(indices, batch_size, out_shape, spatial_shape, ksize, stride, padding,
+                            dilation, out_padding, subm, transpose):
+        outids, pairs, num = get_indice_pairs(indices, batch_size, spatial_shape, ksize, stride,
+                                              padding, dilation, out_padding, bool(subm),
+                                              bool(transpose))
+        return [outids, pairs, num]
+
+    @staticmethod
+    def indice_conv_fp32(features, filters, indice_pairs, indice_pair_num, num_activate_out,
+                         inverse, subm):
+        return indice_conv(features, filters, indice_pairs, indice_pair_num, num_activate_out,
+                           bool(inverse), bool(subm))
+
+    def __getattr__(self, name):
+        raise NotImplementedError("sparse_conv_ext.%s is outside the hot path" % name)
+
+
+sparse_conv_ext = _SparseConvExt()
+
+
+def sparse_to_dense(features, indices, batch_size, spatial_shape, z_major=False):
+    """dense() of a sparse tensor, channels first (structure.py:49-59); z_major=True gives the
+    SparseEncoder output layout [B, C*Z, X, Y] directly (sparse_encoder.py:126-130)."""
+    _C.require_cuda(features, "features", torch.float32)
+    _C.require_cuda(indices, "indices", torch.int32)
+    n, c = features.shape
+    X, Y, Z = (int(v) for v in spatial_shape)
+    dev = features.device
+    with torch.cuda.device(dev):
+        shape = (batch_size, c * Z, X, Y) if z_major else (batch_size, c, X, Y, Z)
+        out = torch.empty(shape, dtype=torch.float32, device=dev)
+        rc = _C.lib().bevb200_sparse_to_dense(_C.ptr(features), _C.ptr(indices), n, c, int(batch_size),
+                                              _vp(_i32([X, Y, Z])), int(bool(z_major)), _C.ptr(out),
+                                              _C.current_stream(dev))
+    _C.check(rc, "sparse_to_dense")
+    return out

@@ -1,0 +1,254 @@
+/*
+ * bevfusion_b200.h -- C ABI of libbevfusion_b200.so (sm_100a / NVIDIA B200).
+ *
+ * Drop-in boundary for the BEVFusion view-transform / LiDAR-voxel hot path of
+ * mit-han-lab/bevfusion (reference tree mounted at /root/reference in the build
+ * container; citations are file:line in that tree).  Every entry point takes plain
+ * device pointers, sizes and a CUDA stream; no torch types cross this boundary.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in _host
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream)
+ *   - return value: 0 on success, negative BEVB200_E* on failure; the failing
+ *     call's message is available from bevb200_last_error() (thread-local)
+ *   - calls are asynchronous on `stream`; none of them synchronises the device
+ *   - no global mutable state: re-entrant across host threads / streams as long
+ *     as the caller gives each in-flight call its own workspace
+ *   - workspaces: query the *_workspace_bytes() function, allocate that many bytes
+ *     (256-B aligned) and pass them in; contents are scratch
+ *   - there is NO CPU fallback anywhere in this library
+ */
+#ifndef BEVFUSION_B200_H_
+#define BEVFUSION_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define BEVB200_API __attribute__((visibility("default")))
+#else
+#define BEVB200_API
+#endif
+
+#define BEVB200_OK 0
+#define BEVB200_EINVAL (-1)    /* bad argument (null pointer, bad size, unsupported shape) */
+#define BEVB200_ECUDA (-2)     /* CUDA runtime / launch error */
+#define BEVB200_EWORKSPACE (-3) /* workspace too small */
+#define BEVB200_EUNSUPPORTED (-4)
+
+BEVB200_API int bevb200_version(void);
+BEVB200_API const char *bevb200_last_error(void);
+/* number of kernels launched by this library on the calling thread since the last
+ * reset (bench.py's "gpu_launches" figure comes from here) */
+BEVB200_API long long bevb200_launch_count(void);
+BEVB200_API void bevb200_reset_launch_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * bev_pool  (reference: mmdet3d/ops/bev_pool/src/bev_pool_cuda.cu, bev_pool_cpu.cpp)
+ * ---------------------------------------------------------------------------------- */
+
+/* Replaces `void bev_pool(int b,int d,int h,int w,int n,int c,int n_intervals,
+ *                         const float* x,const int* geom_feats,const int* interval_starts,
+ *                         const int* interval_lengths,float* out)`
+ * (bev_pool_cuda.cu:86-90, called from bev_pool_forward bev_pool_cpu.cpp:22-47).
+ *   x               [n, c] fp32, rows sorted by rank (the op's contract)
+ *   geom_feats      [n, 4] int32 (x, y, z, b) of each sorted row
+ *   interval_starts [n_intervals], interval_lengths [n_intervals] int32
+ *   out             [b, d, h, w, c] fp32; EVERY element is written (cells without an
+ *                   interval get 0), so the caller need not pre-zero it
+ * Differences from the reference launcher: runs on `stream` (the reference uses the
+ * legacy default stream, bev_pool_cuda.cu:88); sums each interval with a fixed
+ * chunked order (deterministic run to run).
+ * workspace: bevb200_bev_pool_workspace_bytes(n, c). */
+BEVB200_API size_t bevb200_bev_pool_workspace_bytes(int n, int c);
+BEVB200_API int bevb200_bev_pool(int b, int d, int h, int w, int n, int c, int n_intervals,
+                     const float *x, const int32_t *geom_feats,
+                     const int32_t *interval_starts, const int32_t *interval_lengths,
+                     float *out, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Replaces `void bev_pool_grad(...)` (bev_pool_cuda.cu:92-96, called from
+ * bev_pool_backward bev_pool_cpu.cpp:60-87).
+ *   out_grad [b, d, h, w, c] fp32 contiguous -> x_grad [n, c] fp32 (sorted-row order).
+ * Every row of x_grad that belongs to an interval is written; rows not covered by any
+ * interval (none, for intervals produced by the reference's QuickCumsumCuda) are zeroed. */
+BEVB200_API int bevb200_bev_pool_grad(int b, int d, int h, int w, int n, int c, int n_intervals,
+                          const float *out_grad, const int32_t *geom_feats,
+                          const int32_t *interval_starts, const int32_t *interval_lengths,
+                          float *x_grad, void *stream);
+
+/* B200-first variants of the two calls above: rows are read (written) through `perm`,
+ * the sorted->original row map produced by bevb200_bev_pool_prepare_*, so that the
+ * caller never materialises x[kept][argsort] (base.py:168, bev_pool.py:94).
+ *   x / x_grad  [n_total, c] in ORIGINAL (unsorted, unfiltered) order
+ *   perm        [n] int32, perm[i] = original row of sorted row i
+ * bev_pool_grad_perm zero-fills the rows of x_grad that were filtered out. */
+BEVB200_API int bevb200_bev_pool_perm(int b, int d, int h, int w, int n, int c, int n_intervals,
+                          const float *x, const int32_t *perm, const int32_t *geom_feats,
+                          const int32_t *interval_starts, const int32_t *interval_lengths,
+                          float *out, void *workspace, size_t workspace_bytes, void *stream);
+BEVB200_API int bevb200_bev_pool_grad_perm(int b, int d, int h, int w, int n, int n_total, int c,
+                               int n_intervals, const float *out_grad, const int32_t *perm,
+                               const int32_t *geom_feats, const int32_t *interval_starts,
+                               const int32_t *interval_lengths, float *x_grad, void *stream);
+
+/* bev_pool precompute.  Replaces, on device and in one call, the index glue of
+ * BaseTransform.bev_pool (mmdet3d/models/vtransforms/base.py:149-169: quantise, batch
+ * index, bounds mask), bev_pool() (ops/bev_pool/bev_pool.py:87-94: rank, argsort,
+ * gathers) and QuickCumsumCuda.forward (bev_pool.py:41-46: interval table).
+ *
+ *   geom_xyz   [n_total, 3] fp32 lidar-frame frustum points (get_geometry output)
+ *   n_per_batch  n_total / B (batch index of point i is i / n_per_batch, base.py:151-157)
+ *   lower_host[3] = (bx - dx/2) evaluated in fp32 exactly as base.py:149 does,
+ *   dx_host[3], nx_host[3] = grid cells along x, y, z (base.py:15-21)
+ *   idx = trunc_toward_zero((g - lower) / dx) in fp32; kept iff 0 <= idx_k < nx_k
+ *   rank = x*(W*D*B) + y*(D*B) + z*B + b with (B, D, H, W) = (B, nz, nx, ny)
+ * Outputs (all sized for the worst case n_total):
+ *   ranks_sorted [n_total] int32, perm [n_total] int32 (ascending original index
+ *   inside equal ranks -- a stable sort; the reference's argsort is unstable so any
+ *   order is within its contract), geom_sorted [n_total, 4] int32 (x, y, z, b),
+ *   interval_starts / interval_lengths [n_total] int32,
+ *   counts [2] int32 = {n_kept, n_intervals}  (device memory; read it back once)
+ */
+BEVB200_API size_t bevb200_bev_pool_prepare_workspace_bytes(int n_total);
+BEVB200_API int bevb200_bev_pool_prepare_geom(const float *geom_xyz, int n_total, int n_per_batch,
+                                  const float *lower_host, const float *dx_host,
+                                  const int32_t *nx_host, int B, int32_t *ranks_sorted,
+                                  int32_t *perm, int32_t *geom_sorted,
+                                  int32_t *interval_starts, int32_t *interval_lengths,
+                                  int32_t *counts, void *workspace, size_t workspace_bytes,
+                                  void *stream);
+/* Same, starting from already quantised int64 coords [n, 4] = (x, y, z, b) as handed to
+ * bev_pool() (bev_pool.py:84).  Rows outside [0,H)x[0,W)x[0,D)x[0,B) are dropped
+ * (the reference would write out of bounds for them). */
+BEVB200_API int bevb200_bev_pool_prepare_coords(const int64_t *coords, int n, int B, int D, int H, int W,
+                                    int32_t *ranks_sorted, int32_t *perm,
+                                    int32_t *geom_sorted, int32_t *interval_starts,
+                                    int32_t *interval_lengths, int32_t *counts,
+                                    void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * voxelization (reference: mmdet3d/ops/voxel/src/voxelization.h, voxelization_cuda.cu)
+ * ---------------------------------------------------------------------------------- */
+
+/* Replaces voxelization::hard_voxelize_gpu (voxelization_cuda.cu:231-373; bound as
+ * voxel_layer.hard_voxelize, voxelization.h:58-81), deterministic=True semantics:
+ *   - c_k = (int)floor((p_k - min_k) / vs_k) in fp32, valid iff 0 <= c_k < grid_k,
+ *     grid_k = round((max_k - min_k) / vs_k)                 (:37-58, :256-258)
+ *   - voxel ids in order of first appearance by point index; only the first
+ *     max_voxels distinct voxels are kept                     (:149-180)
+ *   - a point's slot = number of earlier points in its voxel; kept iff < max_points
+ *   - voxels[v, slot, :] = points[i, :], coors[v] = (cx, cy, cz) (x,y,z order in this
+ *     fork), num_points_per_voxel[v] = min(count, max_points)
+ * The caller pre-zeroes voxels / coors / num_points_per_voxel at cap size
+ * (voxelize.py:52-54); only used slots are written.  The number of voxels is written to
+ * voxel_num (DEVICE int32[1]) -- the reference returns it as a host int after a device
+ * sync (:369-370); the host wrapper does that read.
+ * No O(N^2) scan, no <<<1,1>>> kernel, no device synchronisation. */
+BEVB200_API size_t bevb200_hard_voxelize_workspace_bytes(int num_points, int max_points);
+BEVB200_API int bevb200_hard_voxelize(const float *points, int num_points, int num_features,
+                          const float *voxel_size_host, const float *coors_range_host,
+                          int max_points, int max_voxels, float *voxels, int32_t *coors,
+                          int32_t *num_points_per_voxel, int32_t *voxel_num,
+                          void *workspace, size_t workspace_bytes, void *stream);
+
+/* Replaces voxelization::dynamic_voxelize_gpu (voxelization_cuda.cu:485-528):
+ * coors[i] = (cx, cy, cz) or (-1,-1,-1) when the point is out of range.  (The reference
+ * kernel only guarantees coors[i][0] == -1 for such points, :38-47.) */
+BEVB200_API int bevb200_dynamic_voxelize(const float *points, int num_points, int num_features,
+                             const float *voxel_size_host, const float *coors_range_host,
+                             int32_t *coors, void *stream);
+
+/* Fused BEVFusion.voxelize glue (mmdet3d/models/fusion_models/bevfusion.py:183,191-195):
+ * feats[v, :] = sum_slot voxels[v, slot, :] / num[v]  and coords[v] = (batch_idx, x, y, z). */
+BEVB200_API int bevb200_voxel_mean(const float *voxels, const int32_t *coors, const int32_t *num_points,
+                       int num_voxels, int max_points, int num_features, int batch_idx,
+                       float *feats, int32_t *coords4, void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * sparse convolution (reference: mmdet3d/ops/spconv/include/spconv/spconv_ops.h,
+ * indice.cu.h, geometry.h, reordering.cu.h)
+ * ---------------------------------------------------------------------------------- */
+
+/* Rulebook.  Replaces spconv::getIndicePair<3> (spconv_ops.h:27-141; bound as
+ * sparse_conv_ext.get_indice_pairs_3d, all.cc:22-27) for transpose == 0.
+ *
+ * The rulebook is produced in offset-major neighbour-table form
+ *     nbr[k * n_out + o] = input row feeding output row o through kernel offset k, or -1
+ * (k = (off_x*K_y + off_y)*K_z + off_z as geometry.h:57-73), which is what the
+ * implicit-GEMM kernel consumes; bevb200_rulebook_to_pairs() converts it to the
+ * reference's indicePairs[K,2,N] / indiceNum[K] layout.
+ *
+ * Two calls because the number of outputs of a strided conv is data dependent:
+ *   1. bevb200_rulebook_prepare: marks the active output sites in a bitmap over the
+ *      dense output grid, ranks them, and writes n_out (device int32[1]).  SubM:
+ *      n_out = n_in and the output sites are the input sites in input order
+ *      (spconv_ops.h:76-101).  Strided: output rows are ordered by ascending flat index
+ *      ((b*X + x)*Y + y)*Z + z -- the order of the reference's GPU path after
+ *      torch::_unique (spconv_ops.h:130-136, indice.cu.h:112-127).
+ *   2. bevb200_rulebook_fill: writes out_indices [n_out, 4] (b, x, y, z) and
+ *      nbr [K, n_out] using the state left in `workspace` by step 1.
+ */
+BEVB200_API size_t bevb200_rulebook_workspace_bytes(int n_in, int batch_size, const int32_t *out_shape_host);
+BEVB200_API int bevb200_rulebook_prepare(const int32_t *indices, int n_in, int batch_size,
+                             const int32_t *spatial_shape_host, const int32_t *out_shape_host,
+                             const int32_t *ksize_host, const int32_t *stride_host,
+                             const int32_t *padding_host, const int32_t *dilation_host,
+                             int subm, int32_t *n_out, void *workspace,
+                             size_t workspace_bytes, void *stream);
+BEVB200_API int bevb200_rulebook_fill(const int32_t *indices, int n_in, int batch_size,
+                          const int32_t *spatial_shape_host, const int32_t *out_shape_host,
+                          const int32_t *ksize_host, const int32_t *stride_host,
+                          const int32_t *padding_host, const int32_t *dilation_host,
+                          int subm, int n_out, int32_t *out_indices, int32_t *nbr,
+                          void *workspace, size_t workspace_bytes, void *stream);
+
+/* nbr[K, n_out] -> indicePairs[K, 2, n_in] (-1 padded) + indiceNum[K]
+ * (layout of spconv_ops.h:53-57).  Pairs of one offset are emitted in ascending output
+ * row (the reference's GPU order is atomic-arrival order, i.e. unspecified). */
+BEVB200_API int bevb200_rulebook_to_pairs(const int32_t *nbr, int kernel_volume, int n_out, int n_in,
+                              int32_t *indice_pairs, int32_t *indice_num, void *stream);
+/* indicePairs[K, 2, n_pairs_dim] + indiceNum[K] -> nbr[K, n_out].  inverse != 0 swaps the
+ * roles of the two pair columns (spconv_ops.h:316,345). */
+BEVB200_API int bevb200_pairs_to_nbr(const int32_t *indice_pairs, const int32_t *indice_num,
+                         int kernel_volume, int pairs_dim, int n_out, int inverse,
+                         int32_t *nbr, void *stream);
+
+/* Sparse convolution forward.  Replaces spconv::indiceConv<float> (spconv_ops.h:260-361;
+ * bound as sparse_conv_ext.indice_conv_fp32) -- the per-offset gather -> mm_out ->
+ * scatter-add loop -- with ONE output-stationary implicit-GEMM kernel:
+ *     out[o, :] = epilogue( sum_k features[nbr[k, o], :] @ weight[k] )
+ *   features [n_in, c_in] fp32, weight [K, c_in, c_out] fp32 (conv.py:100 layout
+ *   [kx,ky,kz,Cin,Cout] flattened), nbr [K, n_out], out [n_out, c_out] fp32.
+ * Optional fused epilogue (all may be NULL / 0), applied in this order:
+ *     y = acc * scale[c] + shift[c]      (folded eval-mode BatchNorm1d / bias)
+ *     y += residual[o, c]                (SparseBasicBlock identity, sparse_block.py:105)
+ *     y = max(y, 0) if relu
+ * precision: BEVB200_PREC_FP32  exact fp32 FFMA accumulation (SIMT)
+ *            BEVB200_PREC_TF32X3 tcgen05 tensor cores, 3xTF32 split (fp32-class accuracy)
+ *            BEVB200_PREC_TF32   tcgen05 single-pass TF32 (fast mode, ~1e-3 rel)
+ */
+#define BEVB200_PREC_FP32 0
+#define BEVB200_PREC_TF32X3 1
+#define BEVB200_PREC_TF32 2
+BEVB200_API int bevb200_spconv_forward(const float *features, const float *weight, const int32_t *nbr,
+                           int n_in, int n_out, int c_in, int c_out, int kernel_volume,
+                           const float *scale, const float *shift, const float *residual,
+                           int relu, int precision, float *out, void *stream);
+
+/* SparseConvTensor.dense() (structure.py:49-59) fused with SparseEncoder's
+ * permute(0,1,4,2,3).view(N, C*D, H, W) (sparse_encoder.py:126-130):
+ *   out[b, c*Z + z, x, y] = features[i, c] for indices[i] = (b, x, y, z); zero elsewhere.
+ * With z_major == 0 the plain channels-first dense layout out[b, c, x, y, z] is written.
+ * out must hold B*C*X*Y*Z floats; it is fully written (zero filled) by the call. */
+BEVB200_API int bevb200_sparse_to_dense(const float *features, const int32_t *indices, int n, int c,
+                            int batch_size, const int32_t *spatial_shape_host, int z_major,
+                            float *out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BEVFUSION_B200_H_ */
