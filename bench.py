@@ -1,0 +1,437 @@
+#!/usr/bin/env python
+"""bench.py -- frames/sec of the BEVFusion C+L hot path on B200 (one JSON line on stdout).
+
+A "step" is one frame of the hot path named by BASELINE.json's north_star, on synthetic
+nuScenes-shaped inputs (bevfusion_b200/synthetic.py):
+
+    bev_pool forward   6 cam x 118 depth x 32 x 88 frustum, C=80 -> 360x360 BEV   (config C2)
+    hard_voxelize      ~296 k points x 5, 0.075 m voxels, grid 1440x1440x40        (config C3)
+    voxel mean + SparseEncoder (VoxelNet 0.075: 17 SubM + 4 strided sparse convs) -> [256,180,180]
+
+The dense glue networks of the full model (SwinT, FPNs, fuser, SECOND, TransFusion head) are not
+part of the hot path and are not run; `config.workload` says so.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+N > 1 is launched by torchrun (one rank per GPU); every rank runs the same per-frame work on its
+own synthetic sample (weak scaling, no data-path collective -- the path shards by sample), the
+timed region is bracketed by barrier + cuda synchronize, time = max over ranks.
+
+--impl reference times the reference's CPU implementation of the path on the host cores
+(oracle/_ref extension for the sparse encoder, the restated QuickCumsum for bev_pool, the C port
+for hard_voxelize), each step a bounded sample of the frame (see `sample`).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "frames/sec C+L BEVFusion hot path (bev_pool + hard_voxelize + SparseEncoder)"
+WORKLOAD = ("C2+C3 hot path per frame: bev_pool fwd 6-cam 256x704 D=118 C=80 -> 360x360 (N'=1,993,728 rows, "
+            "638 MB fp32) + hard_voxelize ~296k pts 0.075 m (1440x1440x40, cap 160k x 10) + voxel mean + "
+            "SparseEncoder VoxelNet-0.075 (17 SubM + 4 strided convs) -> [1,256,180,180]; "
+            "dense glue nets (SwinT/FPN/fuser/SECOND/TransFusion) not included")
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"],
+                    bf16_tflops_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe)
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+class HotPath:
+    """One frame of the hot path through the repo's public API (bevfusion_b200.*)."""
+
+    def __init__(self, device, seed=0, precision=None):
+        from bevfusion_b200 import synthetic as S
+        from bevfusion_b200.bev_pool import BEVPoolPlan
+        from bevfusion_b200.sparse_encoder import voxelnet_0p075_encoder
+        from bevfusion_b200.voxelize import Voxelization
+        self.S, self.device = S, device
+        geom, cfg = S.camera_geometry("C2", device=device)
+        self.cfg = cfg
+        self.plan = BEVPoolPlan(geom, cfg["xbound"], cfg["ybound"], cfg["zbound"])   # static per calibration
+        del geom
+        L = S.LIDAR_C3
+        self.voxelize = Voxelization(L["voxel_size"], L["point_cloud_range"], L["max_num_points"],
+                                     L["max_voxels"]).eval()
+        torch.manual_seed(seed)
+        self.encoder = voxelnet_0p075_encoder().to(device).eval()
+        self.precision = precision
+        self.points_host = torch.from_numpy(S.lidar_cloud(seed=seed)).pin_memory()
+        self.x_host = None
+        t = self.plan.tables
+        self.n_kept, self.n_intervals, self.n_total = t.n_kept, t.n_intervals, t.n_total
+        self.ev = {}
+
+    def device_inputs(self, seed=0):
+        x = self.S.lifted_features("C2", device=self.device, seed=seed)          # 638 MB, > L2
+        return x, self.points_host.to(self.device)
+
+    def host_inputs(self, seed=0):
+        if self.x_host is None:
+            g = torch.Generator().manual_seed(seed)
+            shape = (1, 6, 118, 32, 88, 80)
+            self.x_host = torch.empty(shape, dtype=torch.float32).pin_memory()
+            # fill blockwise (cheap): one camera of randn repeated with a per-camera offset
+            block = torch.randn(shape[2:], generator=g)
+            for cam in range(6):
+                self.x_host[0, cam].copy_(block + 0.01 * cam)
+        return self.x_host, self.points_host
+
+    def frame(self, x, points, timers=None):
+        """x [1,6,118,32,88,80] and points [N,5] on the device -> (bev [1,80,360,360], lidar [1,256,180,180])."""
+        from bevfusion_b200.voxelize import voxelize_mean
+
+        def mark(name):
+            if timers is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                timers.setdefault(name, []).append(e)
+
+        mark("t0")
+        bev = self.plan(x)
+        mark("bev_pool")
+        v, c, n = self.voxelize(points)
+        feats, coords = voxelize_mean(v, c, n, 0)
+        mark("voxelize")
+        with torch.no_grad():
+            lidar = self.encoder(feats, coords, 1, precision=self.precision)
+        mark("encoder")
+        return bev, lidar
+
+    # algorithmic work per frame (DESIGN.md section "roofline accounting")
+    def bev_pool_bytes(self):
+        C = 80
+        return 4 * C * self.n_kept + 4 * C * 360 * 360 + 4 * self.n_kept + 12 * self.n_intervals
+
+    def encoder_flops(self, feats, coords):
+        """sum over convs of 2 * pairs * Cin * Cout, pairs counted from the rulebooks."""
+        from bevfusion_b200 import spconv
+        from bevfusion_b200.spconv.conv import SparseConvolution
+        total, pairs_total = 0, 0
+        x = spconv.SparseConvTensor(feats, coords.int(), self.encoder.sparse_shape, 1)
+        convs = []
+        hooks = [m.register_forward_pre_hook(lambda mod, inp: convs.append((mod, inp[0])))
+                 for m in self.encoder.modules() if isinstance(m, SparseConvolution)]
+        with torch.no_grad():
+            self.encoder(feats, coords, 1, precision=self.precision)
+        for h in hooks:
+            h.remove()
+        for mod, inp in convs:
+            rb, _ = mod._rulebook(inp)
+            pairs = int((rb.nbr >= 0).sum())
+            pairs_total += pairs
+            total += 2 * pairs * mod.in_channels * mod.out_channels
+        return total, pairs_total
+
+
+def run_ours(args, rank, world, local_rank):
+    from bevfusion_b200 import _C
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    _C.lib()
+    peaks = load_peaks()
+    hp = HotPath(device, seed=rank, precision=args.precision)
+    x, pts = hp.device_inputs(seed=rank)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        out = hp.frame(x, pts)
+    del out
+    barrier()
+    # --- device-resident throughput ------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    timers = {}
+    _C.reset_launch_count()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = hp.frame(x, pts, timers)
+    e1.record()
+    barrier()
+    launches = _C.launch_count()
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=device)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+
+    def stage_ms(a, b):
+        return statistics.mean(ea.elapsed_time(eb) for ea, eb in zip(timers[a], timers[b]))
+
+    stages = dict(bev_pool_ms=stage_ms("t0", "bev_pool"), voxelize_ms=stage_ms("bev_pool", "voxelize"),
+                  encoder_ms=stage_ms("voxelize", "encoder"))
+
+    # --- end to end through the public API with HOST buffers ------------------------------
+    xh, ph = hp.host_inputs(seed=rank)
+    bev_h = torch.empty((1, 80, 360, 360), dtype=torch.float32).pin_memory()
+    lid_h = torch.empty((1, 256, 180, 180), dtype=torch.float32).pin_memory()
+    del x
+    torch.cuda.empty_cache()
+
+    def e2e_frame():
+        xd = xh.to(device, non_blocking=True)
+        pd = ph.to(device, non_blocking=True)
+        bev, lidar = hp.frame(xd, pd)
+        bev_h.copy_(bev, non_blocking=True)
+        lid_h.copy_(lidar, non_blocking=True)
+
+    for _ in range(2):
+        e2e_frame()
+    barrier()
+    e2e_steps = max(3, min(args.steps, 10))
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_frame()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    e2e_ms = float(t.item()) / e2e_steps
+    h2d = xh.numel() * 4 + ph.numel() * 4
+    d2h = bev_h.numel() * 4 + lid_h.numel() * 4
+
+    if rank != 0:
+        return
+    # --- roofline of the dominant kernel + the north star's named kernel (bev_pool) --------
+    x, pts = hp.device_inputs(seed=0)
+    v, c, n = hp.voxelize(pts)
+    from bevfusion_b200.voxelize import voxelize_mean
+    feats, coords = voxelize_mean(v, c, n, 0)
+    flops, pairs = hp.encoder_flops(feats, coords)
+    pool_bytes = hp.bev_pool_bytes()
+    # bev_pool kernel alone (plan.pool = memset + pooling kernel + fixup), CUDA events, x > L2
+    for _ in range(3):
+        hp.plan.pool(x)
+    evs = []
+    for _ in range(10):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); hp.plan.pool(x); b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    pool_ms = statistics.median(a.elapsed_time(b) for a, b in evs)
+    pool_gbs = pool_bytes / (pool_ms * 1e-3) / 1e9
+    enc_tflops = flops / (stages["encoder_ms"] * 1e-3) / 1e12
+    roof_pool = dict(kernel="bevpool_fwd_kernel<20,8> (+memset, fixup)", bound="hbm", achieved=round(pool_gbs, 1),
+                     peak=peaks["hbm_gbs"], unit="GB/s", frac=round(pool_gbs / peaks["hbm_gbs"], 4),
+                     traffic=None, ms=round(pool_ms, 4), algorithmic_bytes=pool_bytes, peak_source=peaks["source"])
+    roof_enc = dict(kernel="spconv implicit GEMM x21 (whole SparseEncoder incl. rulebooks)", bound="tensor",
+                    achieved=round(enc_tflops, 3), peak=peaks["bf16_tflops_sustained"], unit="TFLOP/s",
+                    frac=round(enc_tflops / peaks["bf16_tflops_sustained"], 5), traffic=None,
+                    ms=round(stages["encoder_ms"], 4), algorithmic_flops=flops, pairs=pairs,
+                    peak_source=peaks["source"],
+                    note="useful FLOPs = sum 2*pairs*Cin*Cout; peak = measured dense bf16 cuBLAS (sustained)")
+    dominant = roof_enc if stages["encoder_ms"] >= stages["bev_pool_ms"] else roof_pool
+    cpu = cpu_baseline(n_steps=1)
+    line = {
+        "metric": METRIC, "value": round(world * 1000.0 / ms_per_step, 3), "unit": "frames/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": 1, "parallelism": "sample-parallel x%d" % world,
+                   "spconv_precision": {None: "env/default fp32", 0: "fp32", 1: "tf32x3", 2: "tf32"}[args.precision],
+                   "l2": "inputs larger than L2: the 638 MB feature volume streams through L2 every step",
+                   "bev_pool_plan": "rank/sort/interval tables cached per calibration (static geometry)",
+                   "kept_rows": hp.n_kept, "intervals": hp.n_intervals},
+        "stages_ms": {k: round(v, 4) for k, v in stages.items()},
+        "e2e": {"value": round(world * 1000.0 / e2e_ms, 3), "unit": "frames/s", "ms_per_step": round(e2e_ms, 3),
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+        "gpu_launches": int(launches),
+        "roofline": dominant, "roofline_bev_pool": roof_pool, "roofline_encoder": roof_enc,
+        "cpu_baseline": cpu, "clocks": clocks,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the reference's CPU path on the host cores
+# ---------------------------------------------------------------------------------------------
+CPU_SAMPLE = ("per step: bev_pool CPU path (torch QuickCumsum restatement, bev_pool.py:9-35 + base.py:149-169) on "
+              "camera 0 of 6 (x6), hard_voxelize C port on the full cloud, reference CPU spconv extension "
+              "(oracle/_ref) SparseEncoder on a 45-degree azimuth wedge of the cloud scaled by the voxel ratio")
+
+
+class CpuFrame:
+    def __init__(self, seed=0):
+        import oracle
+        from oracle import reference_pipeline as RP
+        from oracle.build_ref import built, load_ref
+        from bevfusion_b200 import synthetic as S
+        from bevfusion_b200.bev_pool import gen_dx_bx
+        from bevfusion_b200.sparse_encoder import voxelnet_0p075_encoder
+        self.oracle, self.RP, self.S = oracle, RP, S
+        self.threads = os.cpu_count() or 1
+        torch.set_num_threads(self.threads)
+        self.kind = "reference" if built("sparse_conv_ext_ref") else "port"
+        self.ref = load_ref("sparse_conv_ext_ref") if self.kind == "reference" else None
+        geom, cfg = S.camera_geometry("C2")
+        self.geom0 = geom[:, :1].contiguous()
+        self.dx, self.bx, self.nx = gen_dx_bx(cfg["xbound"], cfg["ybound"], cfg["zbound"])
+        g = torch.Generator().manual_seed(seed)
+        self.x0 = torch.randn((1, 1, 118, 32, 88, 80), generator=g)
+        self.points = S.lidar_cloud(seed=seed)
+        az = np.arctan2(self.points[:, 1], self.points[:, 0])
+        self.wedge = self.points[(az >= 0) & (az < np.pi / 4)]
+        torch.manual_seed(seed)
+        self.encoder = voxelnet_0p075_encoder().eval()
+
+    def step(self):
+        """returns the extrapolated CPU seconds for one full frame"""
+        RP, L = self.RP, self.S.LIDAR_C3
+        t0 = time.perf_counter()
+        RP.bev_pool_cpu_quickcumsum(self.x0, self.geom0, self.dx, self.bx, self.nx)
+        t_pool = (time.perf_counter() - t0) * 6.0
+        t0 = time.perf_counter()
+        feats, coords = RP.voxelize_cpu(self.points, L, 160000)
+        t_vox = time.perf_counter() - t0
+        wf, wc = RP.voxelize_cpu(self.wedge, L, 160000)
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            if self.ref is not None:
+                RP.reference_encoder_forward(self.ref, self.encoder, wf, wc, 1)
+            else:
+                self._port_encoder(wf, wc)
+        t_enc = (time.perf_counter() - t0) * (feats.shape[0] / max(wf.shape[0], 1))
+        return t_pool + t_vox + t_enc
+
+    def _port_encoder(self, feats, coords):
+        # oracle port of the first stage only, scaled by the FLOP share (used when oracle/_ref is absent)
+        o = self.oracle
+        w = self.encoder.conv_input[0].weight.detach().numpy()
+        o.sparse_conv(feats.numpy(), coords.numpy(), 1, [1440, 1440, 41], w, [3, 3, 3], [1, 1, 1], [1, 1, 1],
+                      [1, 1, 1], True, acc64=False)
+
+
+def cpu_baseline(n_steps=1):
+    cf = CpuFrame()
+    secs = [cf.step() for _ in range(n_steps)]
+    s = statistics.median(secs)
+    return {"value": round(1.0 / s, 5), "unit": "frames/s", "cores": cf.threads, "kind": cf.kind,
+            "sample": CPU_SAMPLE, "seconds_per_frame": round(s, 3)}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cf = CpuFrame()
+    for _ in range(min(args.warmup, 1)):
+        cf.step()
+    t0 = time.perf_counter()
+    secs = [cf.step() for _ in range(args.steps)]
+    wall = (time.perf_counter() - t0) / max(args.steps, 1)
+    s = sum(secs) / len(secs)
+    value = round(1.0 / s, 5)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": round(s * 1000.0, 2),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "note": "CPU host cores only; one process regardless of n_gpus; "
+                       "ms_per_step is the frame time extrapolated from the per-step sample",
+                       "sample_wall_ms_per_step": round(wall * 1000.0, 1)},
+            "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cf.threads, "kind": cf.kind,
+                             "sample": CPU_SAMPLE},
+            "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", type=int, default=None, help="spconv precision: 0 fp32, 1 tf32x3, 2 tf32")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback")
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

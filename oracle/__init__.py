@@ -1,0 +1,257 @@
+"""oracle -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+CPU restatement (numpy + plain C, oracle/oracle.c) of the reference algorithms of the BEVFusion
+hot path.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this package, and only as the checker / reported CPU baseline.  Nothing under
+bevfusion_b200/ imports it.
+
+Pinning (the reference tree ships no tests or golden vectors for this path):
+  * tests/golden/*.npz hold outputs of the reference's OWN code run in the build container:
+    its compiled CPU extensions (oracle/_ref, built unmodified from /root/reference by
+    oracle/build_ref.py) for voxelization and spconv, and its pure-torch QuickCumsum
+    (mmdet3d/ops/bev_pool/bev_pool.py:9-35, the only CPU-capable bev_pool path) for pooling;
+    tests/test_oracle_golden.py checks this oracle against them;
+  * on the GPU box the tests additionally compare against the reference CUDA kernels
+    themselves (oracle/_ref/*.so travel with the repo snapshot).
+
+Each function cites the reference file:line it follows (paths relative to /root/reference).
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+_lib = None
+
+
+def build():
+    """Compile oracle.c -> liboracle.so (gcc, seconds)."""
+    src = os.path.join(_HERE, "oracle.c")
+    if not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "liboracle.so"])
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(_LIB_PATH)
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _ivec(v):
+    return (ctypes.c_int * len(v))(*[int(x) for x in v])
+
+
+def _fvec(v):
+    return (ctypes.c_float * len(v))(*[float(x) for x in v])
+
+
+# ------------------------------------------------------------------------------------ bev_pool
+def gen_dx_bx(xbound, ybound, zbound):
+    """mmdet3d/models/vtransforms/base.py:15-21 (fp32 dx, bx; integer nx by truncation)."""
+    rows = [xbound, ybound, zbound]
+    dx = np.array([r[2] for r in rows], dtype=np.float32)
+    bx = np.array([r[0] + r[2] / 2.0 for r in rows], dtype=np.float32)
+    nx = np.array([int((r[1] - r[0]) / r[2]) for r in rows], dtype=np.int64)
+    return dx, bx, nx
+
+
+def quantize_filter(geom, dx, bx, nx, B):
+    """base.py:149-169: ((geom - (bx - dx/2)) / dx).long(), batch index column, bounds mask.
+    geom [N', 3] fp32 -> coords [N', 4] int64 (x, y, z, b), kept [N'] bool."""
+    geom = _f32(geom).reshape(-1, 3)
+    lower = (bx.astype(np.float32) - dx.astype(np.float32) / np.float32(2.0)).astype(np.float32)
+    q = ((geom - lower) / dx.astype(np.float32))
+    with np.errstate(invalid="ignore"):
+        idx = np.trunc(q).astype(np.int64)  # .long(): truncation toward zero
+    n = geom.shape[0]
+    batch_ix = (np.arange(n, dtype=np.int64) // (n // B)).reshape(-1, 1)
+    coords = np.concatenate([idx, batch_ix], axis=1)
+    kept = ((coords[:, 0] >= 0) & (coords[:, 0] < nx[0]) & (coords[:, 1] >= 0)
+            & (coords[:, 1] < nx[1]) & (coords[:, 2] >= 0) & (coords[:, 2] < nx[2])
+            & np.isfinite(q).all(axis=1))
+    return coords, kept
+
+
+def ranks_of(coords, B, D, H, W):
+    """mmdet3d/ops/bev_pool/bev_pool.py:87-92."""
+    c = coords.astype(np.int64)
+    return c[:, 0] * (W * D * B) + c[:, 1] * (D * B) + c[:, 2] * B + c[:, 3]
+
+
+def sort_and_intervals(ranks):
+    """bev_pool.py:93 (argsort; stable here) and :41-46 (interval table)."""
+    order = np.argsort(ranks, kind="stable")
+    rs = ranks[order]
+    kept = np.ones(rs.shape[0], dtype=bool)
+    kept[1:] = rs[1:] != rs[:-1]
+    starts = np.nonzero(kept)[0].astype(np.int32)
+    lengths = np.empty_like(starts)
+    if starts.size:
+        lengths[:-1] = starts[1:] - starts[:-1]
+        lengths[-1] = rs.shape[0] - starts[-1]
+    return order, rs, starts, lengths
+
+
+def bev_pool_forward(x, geom_feats, interval_lengths, interval_starts, b, d, h, w, acc64=True):
+    """bev_pool_forward, bev_pool_cpu.cpp:22-47 + kernel bev_pool_cuda.cu:20-42 -> [b,d,h,w,c]."""
+    x, g = _f32(x), _i32(geom_feats)
+    s, l = _i32(interval_starts), _i32(interval_lengths)
+    n, c = x.shape
+    out = np.zeros((b, d, h, w, c), dtype=np.float32)
+    lib().oracle_bev_pool(int(b), int(d), int(h), int(w), int(n), int(c), int(s.shape[0]), _p(x),
+                          _p(g), _p(s), _p(l), int(acc64), _p(out))
+    return out
+
+
+def bev_pool_backward(out_grad, geom_feats, interval_lengths, interval_starts, b, d, h, w):
+    """bev_pool_backward, bev_pool_cpu.cpp:60-87 + kernel bev_pool_cuda.cu:61-84 -> [n, c]."""
+    og, g = _f32(out_grad), _i32(geom_feats)
+    s, l = _i32(interval_starts), _i32(interval_lengths)
+    n, c = g.shape[0], og.shape[4]
+    xg = np.zeros((n, c), dtype=np.float32)
+    lib().oracle_bev_pool_grad(int(b), int(d), int(h), int(w), int(n), int(c), int(s.shape[0]),
+                               _p(og), _p(g), _p(s), _p(l), _p(xg))
+    return xg
+
+
+def bev_pool(feats, coords, B, D, H, W, acc64=True):
+    """bev_pool(), bev_pool.py:84-98 -> [B, C, D, H, W]."""
+    ranks = ranks_of(coords, B, D, H, W)
+    order, rs, starts, lengths = sort_and_intervals(ranks)
+    x = _f32(feats)[order]
+    g = coords[order].astype(np.int32)
+    out = bev_pool_forward(x, g, lengths, starts, B, D, H, W, acc64)
+    return np.ascontiguousarray(out.transpose(0, 4, 1, 2, 3))
+
+
+def quick_cumsum(x_sorted, ranks_sorted):
+    """QuickCumsum.forward, bev_pool.py:9-24 (the reference's only CPU-capable pooling path):
+    fp32 cumsum, keep last row of each run, adjacent difference.  Returns [n_intervals, c]."""
+    cs = np.cumsum(_f32(x_sorted), axis=0, dtype=np.float32)
+    kept = np.ones(cs.shape[0], dtype=bool)
+    kept[:-1] = ranks_sorted[1:] != ranks_sorted[:-1]
+    cs = cs[kept]
+    return np.concatenate([cs[:1], cs[1:] - cs[:-1]], axis=0)
+
+
+# -------------------------------------------------------------------------------- voxelization
+def hard_voxelize(points, voxel_size, coors_range, max_points, max_voxels):
+    """hard_voxelize_cpu, voxelization_cpu.cpp:107-144 -> (voxels [M,P,F], coors [M,3] (x,y,z),
+    num_points [M], voxel_num)."""
+    pts = _f32(points)
+    n, nf = pts.shape
+    voxels = np.zeros((max_voxels, max_points, nf), dtype=np.float32)
+    coors = np.zeros((max_voxels, 3), dtype=np.int32)
+    num = np.zeros((max_voxels,), dtype=np.int32)
+    m = lib().oracle_hard_voxelize(_p(pts), int(n), int(nf), _fvec(voxel_size), _fvec(coors_range),
+                                   int(max_points), int(max_voxels), _p(voxels), _p(coors), _p(num))
+    assert m >= 0
+    return voxels[:m], coors[:m], num[:m], m
+
+
+def dynamic_voxelize(points, voxel_size, coors_range):
+    """dynamic_voxelize_cpu, voxelization_cpu.cpp:146-171 -> coors [N,3] (-1 rows when OOR)."""
+    pts = _f32(points)
+    n, nf = pts.shape
+    coors = np.zeros((n, 3), dtype=np.int32)
+    lib().oracle_dynamic_voxelize(_p(pts), int(n), int(nf), _fvec(voxel_size), _fvec(coors_range),
+                                  _p(coors))
+    return coors
+
+
+def voxel_mean(voxels, num_points):
+    """BEVFusion.voxelize, bevfusion.py:191-195: feats.sum(dim=1) / sizes."""
+    return (voxels.astype(np.float64).sum(axis=1) / num_points.reshape(-1, 1)).astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------- spconv
+def conv_output_size(input_size, kernel_size, stride, padding, dilation):
+    """get_conv_output_size, mmdet3d/ops/spconv/ops.py:20-31."""
+    return [(input_size[i] + 2 * padding[i] - dilation[i] * (kernel_size[i] - 1) - 1) // stride[i] + 1
+            for i in range(len(input_size))]
+
+
+def get_indice_pairs(indices, batch_size, spatial_shape, ksize, stride, padding, dilation, subm):
+    """getIndicePair<3> CPU branch, spconv_ops.h:27-141 -> (outids [M,4], indice_pairs [K,2,N],
+    indice_num [K], out_shape).  Strided convs number outputs in first-encounter order
+    (geometry.h:144-194); the reference GPU path orders them by ascending flat index."""
+    ind = _i32(indices)
+    n = ind.shape[0]
+    kvol = int(np.prod(ksize))
+    pairs = np.full((kvol, 2, n), -1, dtype=np.int32)
+    num = np.zeros((kvol,), dtype=np.int32)
+    if subm:
+        out_shape = list(spatial_shape)
+        lib().oracle_indice_pairs_subm(_p(ind), n, _ivec(ksize), _ivec(dilation), _ivec(out_shape),
+                                       _p(pairs), _p(num))
+        return ind.copy(), pairs, num, out_shape
+    out_shape = conv_output_size(spatial_shape, ksize, stride, padding, dilation)
+    outids = np.zeros((max(n * kvol, 1), 4), dtype=np.int32)
+    m = lib().oracle_indice_pairs_conv(_p(ind), n, _ivec(ksize), _ivec(stride), _ivec(padding),
+                                       _ivec(dilation), _ivec(out_shape), _p(outids), _p(pairs),
+                                       _p(num))
+    assert m >= 0
+    return outids[:m].copy(), pairs, num, out_shape
+
+
+def indice_conv(features, filters, indice_pairs, indice_num, num_act_out, inverse=False,
+                subm=False, acc64=True):
+    """indiceConv<float>, spconv_ops.h:260-361 -> [num_act_out, Cout]."""
+    f, w = _f32(features), _f32(filters)
+    n_in, c_in = f.shape
+    c_out = w.shape[-1]
+    pairs, num = _i32(indice_pairs), _i32(indice_num)
+    kvol, _, pdim = pairs.shape
+    out = np.zeros((num_act_out, c_out), dtype=np.float32)
+    lib().oracle_indice_conv(_p(f), _p(w), _p(pairs), _p(num), int(n_in), int(num_act_out),
+                             int(c_in), int(c_out), int(kvol), int(pdim), int(subm), int(inverse),
+                             int(acc64), _p(out))
+    return out
+
+
+def flat_index(outids, out_shape):
+    """((b*X + x)*Y + y)*Z + z -- the order of the reference GPU rulebook (indice.cu.h:59-60)."""
+    o = outids.astype(np.int64)
+    return ((o[:, 0] * out_shape[0] + o[:, 1]) * out_shape[1] + o[:, 2]) * out_shape[2] + o[:, 3]
+
+
+def sparse_conv(features, indices, batch_size, spatial_shape, filters, ksize, stride, padding,
+                dilation, subm, acc64=True):
+    """SparseConvolution.forward core (conv.py:152-216) with outputs re-ordered to ascending
+    flat index for strided convs.  Returns (out_features, outids, out_shape)."""
+    outids, pairs, num, out_shape = get_indice_pairs(indices, batch_size, spatial_shape, ksize,
+                                                     stride, padding, dilation, subm)
+    out = indice_conv(features, filters.reshape(-1, filters.shape[-2], filters.shape[-1]), pairs,
+                      num, outids.shape[0], False, subm, acc64)
+    if not subm:
+        order = np.argsort(flat_index(outids, out_shape), kind="stable")
+        out, outids = out[order], outids[order]
+    return out, outids, out_shape
+
+
+def dense(features, indices, batch_size, spatial_shape):
+    """SparseConvTensor.dense(), structure.py:49-59 -> [B, C, X, Y, Z]."""
+    X, Y, Z = spatial_shape
+    c = features.shape[1]
+    out = np.zeros((batch_size, X, Y, Z, c), dtype=features.dtype)
+    idx = indices.astype(np.int64)
+    out[idx[:, 0], idx[:, 1], idx[:, 2], idx[:, 3]] = features
+    return np.ascontiguousarray(out.transpose(0, 4, 1, 2, 3))

@@ -1,0 +1,210 @@
+"""GPU parity tests for bev_pool: CUDA path (through the C ABI) vs the CPU oracle, the committed
+golden fixture, and the reference's own CUDA kernels (oracle/_ref) when present.
+Tolerances: ranks / perm / interval tables bit-exact; pooled features <= 1e-4 relative
+(BASELINE.json north_star); backward is a pure copy -> bit-exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from conftest import ref_module
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(got, gold):
+    return float(np.abs(got.astype(np.float64) - gold.astype(np.float64)).max() / max(np.abs(gold).max(), 1e-30))
+
+
+def random_case(n, c, B, D, H, W, seed, hot_cells=0):
+    rng = np.random.default_rng(seed)
+    coords = np.stack([rng.integers(0, H, n), rng.integers(0, W, n), rng.integers(0, D, n),
+                       rng.integers(0, B, n)], 1).astype(np.int64)
+    if hot_cells:  # a few cells that collect very long intervals (> 2 chunks)
+        hot = rng.integers(0, n, size=n // 3)
+        coords[hot] = coords[rng.integers(0, n, hot_cells)][rng.integers(0, hot_cells, hot.size)]
+    feats = rng.standard_normal((n, c)).astype(np.float32)
+    return feats, coords
+
+
+def sorted_inputs(feats, coords, B, D, H, W):
+    ranks = oracle.ranks_of(coords, B, D, H, W)
+    order, rs, starts, lengths = oracle.sort_and_intervals(ranks)
+    return feats[order], coords[order].astype(np.int32), rs, starts, lengths, order
+
+
+@pytest.mark.parametrize("c", [80, 64, 128, 16, 32, 96, 160, 256, 20, 7])
+def test_forward_ext_vs_oracle(cuda, c):
+    from bevfusion_b200.bev_pool import bev_pool_ext
+    B, D, H, W = 2, 2, 24, 20
+    feats, coords = random_case(30000, c, B, D, H, W, seed=c, hot_cells=3)
+    x, g, rs, starts, lengths, _ = sorted_inputs(feats, coords, B, D, H, W)
+    assert lengths.max() > 600          # exercises the long-interval (multi-chunk) path
+    gold = oracle.bev_pool_forward(x, g, lengths, starts, B, D, H, W, acc64=True)
+    out = bev_pool_ext.bev_pool_forward(torch.from_numpy(x).to(cuda), torch.from_numpy(g).to(cuda),
+                                        torch.from_numpy(lengths).to(cuda),
+                                        torch.from_numpy(starts).to(cuda), B, D, H, W)
+    assert tuple(out.shape) == (B, D, H, W, c)
+    assert rel_err(out.cpu().numpy(), gold) <= 1e-4
+    # run-to-run bit reproducibility (no float atomics)
+    out2 = bev_pool_ext.bev_pool_forward(torch.from_numpy(x).to(cuda), torch.from_numpy(g).to(cuda),
+                                         torch.from_numpy(lengths).to(cuda),
+                                         torch.from_numpy(starts).to(cuda), B, D, H, W)
+    assert torch.equal(out, out2)
+
+
+def test_backward_ext_vs_oracle_bit_exact(cuda):
+    from bevfusion_b200.bev_pool import bev_pool_ext
+    B, D, H, W, c = 2, 1, 16, 12, 80
+    feats, coords = random_case(9000, c, B, D, H, W, seed=11, hot_cells=2)
+    x, g, rs, starts, lengths, _ = sorted_inputs(feats, coords, B, D, H, W)
+    og = np.random.default_rng(1).standard_normal((B, D, H, W, c)).astype(np.float32)
+    gold = oracle.bev_pool_backward(og, g, lengths, starts, B, D, H, W)
+    got = bev_pool_ext.bev_pool_backward(torch.from_numpy(og).to(cuda), torch.from_numpy(g).to(cuda),
+                                         torch.from_numpy(lengths).to(cuda),
+                                         torch.from_numpy(starts).to(cuda), B, D, H, W)
+    assert np.array_equal(got.cpu().numpy(), gold)
+
+
+def test_tables_bit_exact_vs_oracle(cuda):
+    """rank / stable sort / interval table computed by the library == oracle (bit-exact)."""
+    from bevfusion_b200.bev_pool import prepare_from_coords
+    B, D, H, W = 3, 2, 40, 33
+    _, coords = random_case(50000, 4, B, D, H, W, seed=5, hot_cells=2)
+    t = prepare_from_coords(torch.from_numpy(coords).to(cuda), B, D, H, W)
+    ranks = oracle.ranks_of(coords, B, D, H, W)
+    order, rs, starts, lengths = oracle.sort_and_intervals(ranks)
+    assert t.n_kept == coords.shape[0] and t.n_intervals == starts.shape[0]
+    assert np.array_equal(t.ranks[:t.n_kept].cpu().numpy(), rs.astype(np.int32))
+    assert np.array_equal(t.perm[:t.n_kept].cpu().numpy(), order.astype(np.int32))   # stable
+    assert np.array_equal(t.geom.cpu().numpy(), coords[order].astype(np.int32))
+    assert np.array_equal(t.starts.cpu().numpy(), starts)
+    assert np.array_equal(t.lengths.cpu().numpy(), lengths)
+
+
+def test_geometry_quantise_filter_bit_exact(cuda):
+    """quantise + filter + rank from fp32 geometry (base.py:149-169) is bit-exact."""
+    from bevfusion_b200 import synthetic as S
+    from bevfusion_b200.bev_pool import gen_dx_bx, prepare_from_geometry
+    geom, cfg = S.camera_geometry("tiny", batch=2)
+    g = geom.clone()
+    g.view(-1, 3)[:200, 0] = -16.0 - 1e-4        # in (-1, 0): truncates to cell 0 and is KEPT
+    g.view(-1, 3)[200:300, 1] = 16.0             # exactly on the upper bound: dropped
+    dx, bx, nx = gen_dx_bx(cfg["xbound"], cfg["ybound"], cfg["zbound"])
+    t = prepare_from_geometry(g.to(cuda), dx, bx, nx, 2)
+    odx, obx, onx = oracle.gen_dx_bx(cfg["xbound"], cfg["ybound"], cfg["zbound"])
+    coords, kept = oracle.quantize_filter(g.numpy(), odx, obx, onx, 2)
+    ranks = oracle.ranks_of(coords[kept], 2, int(onx[2]), int(onx[0]), int(onx[1]))
+    order, rs, starts, lengths = oracle.sort_and_intervals(ranks)
+    kept_idx = np.nonzero(kept)[0]
+    assert t.n_kept == int(kept.sum()) and t.n_intervals == starts.shape[0]
+    assert np.array_equal(t.ranks[:t.n_kept].cpu().numpy(), rs.astype(np.int32))
+    assert np.array_equal(t.perm[:t.n_kept].cpu().numpy(), kept_idx[order].astype(np.int32))
+    assert np.array_equal(np.sort(t.perm[t.n_kept:].cpu().numpy()), np.nonzero(~kept)[0])
+    assert np.array_equal(t.starts.cpu().numpy(), starts)
+    assert np.array_equal(t.lengths.cpu().numpy(), lengths)
+    assert np.array_equal(t.geom.cpu().numpy(), coords[kept][order].astype(np.int32))
+
+
+def test_drop_in_bev_pool_forward_backward(cuda):
+    """bev_pool(feats, coords, B, D, H, W) -> [B, C, D, H, W]; autograd gives grads in the
+    caller's row order."""
+    from bevfusion_b200.bev_pool import bev_pool
+    B, D, H, W, c = 2, 2, 12, 10, 16
+    feats, coords = random_case(6000, c, B, D, H, W, seed=3)
+    gold = oracle.bev_pool(feats, coords, B, D, H, W)
+    x = torch.from_numpy(feats).to(cuda).requires_grad_(True)
+    out = bev_pool(x, torch.from_numpy(coords).to(cuda), B, D, H, W)
+    assert tuple(out.shape) == (B, c, D, H, W)
+    assert rel_err(out.detach().cpu().numpy(), gold) <= 1e-4
+    w = torch.randn_like(out)
+    (out * w).sum().backward()
+    wn = w.cpu().numpy()
+    gold_grad = wn[coords[:, 3], :, coords[:, 2], coords[:, 0], coords[:, 1]]
+    assert np.array_equal(x.grad.cpu().numpy(), gold_grad)
+
+
+def test_golden_fixture(cuda, golden_dir):
+    """the committed reference-QuickCumsum fixture (tests/golden/make_golden.py)."""
+    from bevfusion_b200.bev_pool import bev_pool
+    g = np.load(os.path.join(golden_dir, "bev_pool_quickcumsum.npz"))
+    B, D, H, W = (int(v) for v in g["dims"])
+    out = bev_pool(torch.from_numpy(g["feats"]).to(cuda), torch.from_numpy(g["coords"]).to(cuda),
+                   B, D, H, W).cpu().numpy()
+    pg = g["pooled_geom"]
+    got = out[pg[:, 3], :, pg[:, 2], pg[:, 0], pg[:, 1]]
+    assert np.abs(got - g["pooled"]).max() < 5e-4       # QuickCumsum's own cancellation error
+
+
+def test_empty_and_single(cuda):
+    from bevfusion_b200.bev_pool import bev_pool, bev_pool_ext
+    z = bev_pool_ext.bev_pool_forward(torch.zeros(0, 80, device=cuda),
+                                      torch.zeros(0, 4, dtype=torch.int32, device=cuda),
+                                      torch.zeros(0, dtype=torch.int32, device=cuda),
+                                      torch.zeros(0, dtype=torch.int32, device=cuda), 1, 1, 4, 4)
+    assert float(z.abs().sum()) == 0 and tuple(z.shape) == (1, 1, 4, 4, 80)
+    out = bev_pool(torch.ones(1, 80, device=cuda), torch.tensor([[3, 2, 0, 0]], device=cuda), 1, 1, 4, 4)
+    assert float(out.sum()) == 80 and float(out[0, :, 0, 3, 2].sum()) == 80
+
+
+def test_vs_reference_cuda_kernel(cuda):
+    """the reference's own bev_pool CUDA kernels, compiled unmodified for sm_100."""
+    ref = ref_module("bev_pool_ext_ref")
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    from bevfusion_b200.bev_pool import bev_pool_ext
+    B, D, H, W, c = 1, 1, 64, 64, 80
+    feats, coords = random_case(200000, c, B, D, H, W, seed=21, hot_cells=4)
+    x, g, rs, starts, lengths, _ = sorted_inputs(feats, coords, B, D, H, W)
+    args = [torch.from_numpy(a).to(cuda) for a in (x, g, lengths, starts)]
+    torch.cuda.synchronize()
+    ref_out = ref.bev_pool_forward(*args, B, D, H, W)      # legacy default stream
+    torch.cuda.synchronize()
+    out = bev_pool_ext.bev_pool_forward(*args, B, D, H, W)
+    assert rel_err(out.cpu().numpy(), ref_out.cpu().numpy()) <= 1e-4
+    og = torch.randn(B, D, H, W, c, device=cuda)
+    torch.cuda.synchronize()
+    ref_g = ref.bev_pool_backward(og, args[1], args[2], args[3], B, D, H, W)
+    torch.cuda.synchronize()
+    got_g = bev_pool_ext.bev_pool_backward(og, args[1], args[2], args[3], B, D, H, W)
+    assert torch.equal(ref_g, got_g)
+
+
+def test_plan_full_size_c2_properties(cuda):
+    """BASELINE config C2 (6 cam, 32x88 features, D=118, C=80, 360x360): plan path vs a float64
+    torch index_add_ gold on the device, plus size-independent properties (mass conservation,
+    linearity) and reference-path equivalence."""
+    from bevfusion_b200 import synthetic as S
+    from bevfusion_b200.bev_pool import BEVPoolPlan
+    geom, cfg = S.camera_geometry("C2", device=cuda)
+    plan = BEVPoolPlan(geom, cfg["xbound"], cfg["ybound"], cfg["zbound"])
+    t = plan.tables
+    assert t.n_total == 6 * 118 * 32 * 88
+    x = S.lifted_features("C2", device=cuda, seed=0)
+    out = plan.pool(x)                                    # [1, 1, 360, 360, 80]
+    xf = x.reshape(-1, 80)
+    perm = t.perm[:t.n_kept].long()
+    # gold: float64 scatter-add by cell on the device
+    cell = (t.geom[:, 0].long() * 360 + t.geom[:, 1].long())
+    gold = torch.zeros(360 * 360, 80, dtype=torch.float64, device=cuda)
+    gold.index_add_(0, cell, xf[perm].double())
+    err = (out.reshape(-1, 80).double() - gold).abs().max() / gold.abs().max()
+    assert float(err) <= 1e-4
+    # mass conservation: sum of the grid == sum of the kept rows
+    assert abs(float(out.double().sum() - xf[perm].double().sum())) <= 1e-6 * float(xf[perm].double().abs().sum())
+    # linearity: pool(2x) == 2 pool(x) exactly (power-of-two scaling is exact in fp32)
+    assert torch.equal(plan.pool(x * 2.0), out * 2.0)
+    # layout of the module-level call == BaseTransform.bev_pool
+    bev = plan(x)
+    assert tuple(bev.shape) == (1, 80, 360, 360)
+    assert torch.equal(bev[0, :, 17, 200], out[0, 0, 17, 200, :])
+    # backward: grad of sum(out * w) w.r.t. x is w[cell] for kept rows, 0 for dropped rows
+    xg = x.clone().requires_grad_(True)
+    w = torch.randn_like(out)
+    (plan.pool(xg) * w).sum().backward()
+    gflat = xg.grad.reshape(-1, 80)
+    assert torch.equal(gflat[perm], w.reshape(-1, 80)[cell])
+    dropped = t.perm[t.n_kept:].long()
+    assert float(gflat[dropped].abs().sum()) == 0.0

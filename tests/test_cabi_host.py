@@ -1,0 +1,96 @@
+"""CPU: the C-ABI library loads and exports every symbol the header declares; host-side logic
+(shape arithmetic, module structure, argument validation).  No compute calls."""
+import numpy as np
+import pytest
+import torch
+
+
+def test_library_exports_every_declared_symbol():
+    from bevfusion_b200 import _C
+    L = _C.lib()
+    declared = _C.declared_symbols()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(L, name), "missing export: " + name
+    assert set(declared) == set(_C._SIGNATURES), "ctypes table out of sync with the header"
+    assert L.bevb200_version() >= 100
+
+
+def test_no_cpu_fallback():
+    """CPU tensors must raise, not silently compute (north star: no CPU fallback)."""
+    from bevfusion_b200.bev_pool import bev_pool, bev_pool_ext
+    from bevfusion_b200.voxelize import Voxelization
+    from bevfusion_b200.spconv import ops
+    with pytest.raises(RuntimeError):
+        bev_pool(torch.zeros(4, 16), torch.zeros(4, 4, dtype=torch.long), 1, 1, 2, 2)
+    with pytest.raises(RuntimeError):
+        bev_pool_ext.bev_pool_forward(torch.zeros(4, 16), torch.zeros(4, 4, dtype=torch.int32),
+                                      torch.ones(1, dtype=torch.int32), torch.zeros(1, dtype=torch.int32),
+                                      1, 1, 2, 2)
+    vox = Voxelization([0.5, 0.5, 0.5], [0, 0, 0, 4, 4, 4], 5, (10, 10)).eval()
+    with pytest.raises(RuntimeError):
+        vox(torch.zeros(8, 4))
+    with pytest.raises(RuntimeError):
+        ops.get_indice_pairs(torch.zeros(3, 4, dtype=torch.int32), 1, [4, 4, 4], 3, 1, 1, 1, 0, True)
+
+
+def test_product_does_not_import_oracle():
+    import glob, os, re
+    root = os.path.join(os.path.dirname(__file__), "..", "bevfusion_b200")
+    for path in glob.glob(os.path.join(root, "**", "*.py"), recursive=True):
+        src = open(path).read()
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), path
+
+
+def test_conv_output_size_matches_reference_formula():
+    from bevfusion_b200.spconv import ops
+    import oracle
+    for shape, k, s, p in [([1440, 1440, 41], [3, 3, 3], [2, 2, 2], [1, 1, 1]),
+                           ([360, 360, 11], [3, 3, 3], [2, 2, 2], [1, 1, 0]),
+                           ([180, 180, 5], [1, 1, 3], [1, 1, 2], [0, 0, 0])]:
+        assert ops.get_conv_output_size(shape, k, s, p, [1, 1, 1]) == oracle.conv_output_size(
+            shape, k, s, p, [1, 1, 1])
+    assert ops.get_conv_output_size([1440, 1440, 41], [3] * 3, [2] * 3, [1] * 3, [1] * 3) == [720, 720, 21]
+    assert ops.get_conv_output_size([180, 180, 5], [1, 1, 3], [1, 1, 2], [0] * 3, [1] * 3) == [180, 180, 2]
+
+
+def test_sparse_encoder_structure_and_state_dict():
+    from bevfusion_b200.sparse_encoder import voxelnet_0p075_encoder
+    from bevfusion_b200.spconv import SparseConv3d, SubMConv3d
+    from bevfusion_b200.sparse_block import SparseBasicBlock
+    m = voxelnet_0p075_encoder()
+    sd = m.state_dict()
+    # names / shapes of the reference checkpoint layout (sparse_encoder.py:63-97, 214-216)
+    assert tuple(sd["conv_input.0.weight"].shape) == (3, 3, 3, 5, 16)
+    assert tuple(sd["encoder_layers.encoder_layer1.0.conv1.weight"].shape) == (3, 3, 3, 16, 16)
+    assert tuple(sd["encoder_layers.encoder_layer1.2.0.weight"].shape) == (3, 3, 3, 16, 32)
+    assert tuple(sd["encoder_layers.encoder_layer3.2.0.weight"].shape) == (3, 3, 3, 64, 128)
+    assert tuple(sd["conv_out.0.weight"].shape) == (1, 1, 3, 128, 128)
+    assert "encoder_layers.encoder_layer4.1.bn2.running_var" in sd
+    convs = [mod for mod in m.modules() if isinstance(mod, (SparseConv3d, SubMConv3d))]
+    assert sum(isinstance(c, SubMConv3d) for c in convs) == 17          # 17 SubM + 4 strided
+    assert sum(not c.subm for c in convs) == 4
+    assert sum(isinstance(b, SparseBasicBlock) for b in m.modules()) == 8
+    down3 = m.encoder_layers.encoder_layer3[2][0]
+    assert down3.padding == [1, 1, 0] and down3.stride == [2, 2, 2]
+    assert m.conv_out[0].kernel_size == [1, 1, 3] and m.conv_out[0].stride == [1, 1, 2]
+    bn = m.conv_input[1]
+    assert bn.eps == 1e-3 and abs(bn.momentum - 0.01) < 1e-12
+
+
+def test_gen_dx_bx_matches_reference_arithmetic():
+    from bevfusion_b200.bev_pool import gen_dx_bx
+    import oracle
+    dx, bx, nx = gen_dx_bx([-54.0, 54.0, 0.3], [-54.0, 54.0, 0.3], [-10.0, 10.0, 20.0])
+    odx, obx, onx = oracle.gen_dx_bx([-54.0, 54.0, 0.3], [-54.0, 54.0, 0.3], [-10.0, 10.0, 20.0])
+    assert np.array_equal(dx.numpy(), odx) and np.array_equal(bx.numpy(), obx)
+    assert nx.tolist() == onx.tolist() == [360, 360, 1]
+
+
+def test_geometry_and_synthetic_shapes():
+    from bevfusion_b200 import synthetic as S
+    geom, cfg = S.camera_geometry("tiny")
+    assert tuple(geom.shape) == (1, 2, 20, 8, 22, 3)
+    pts = S.lidar_cloud(seed=0, sweeps=2)
+    assert pts.shape[1] == 5 and pts.dtype == np.float32
+    assert len(np.arange(*S.CONFIGS["C2"]["dbound"])) == 118

@@ -1,0 +1,106 @@
+"""CPU: pins the oracle (oracle/) against fixtures produced by the reference's own code
+(tests/golden/make_golden.py)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+
+
+@pytest.mark.parametrize("name", ["a", "b", "c"])
+def test_hard_voxelize_matches_reference_cpu(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, "voxelize_%s.npz" % name))
+    v, c, n, m = oracle.hard_voxelize(g["points"], g["voxel_size"], g["coors_range"],
+                                      int(g["max_points"]), int(g["max_voxels"]))
+    assert m == int(g["voxel_num"])
+    assert np.array_equal(c, g["coors"])          # bit-exact coords and order
+    assert np.array_equal(n, g["num_points"])     # bit-exact counts
+    assert np.array_equal(v, g["voxels"])         # bit-exact point payloads / slots
+    dyn = oracle.dynamic_voxelize(g["points"], g["voxel_size"], g["coors_range"])
+    ref = g["dyn_coors"]
+    assert np.array_equal(dyn[:, 0] == -1, ref[:, 0] == -1)
+    ok = ref[:, 0] != -1
+    assert np.array_equal(dyn[ok], ref[ok])
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden",
+                                                                "spconv_*.npz"))))
+def test_spconv_matches_reference_cpu(path):
+    g = np.load(path)
+    outids, pairs, num, out_shape = oracle.get_indice_pairs(
+        g["indices"], int(g["batch_size"]), list(g["spatial_shape"]), list(g["ksize"]),
+        list(g["stride"]), list(g["padding"]), [1, 1, 1], bool(g["subm"]))
+    assert out_shape == list(g["out_shape"])
+    assert np.array_equal(outids, g["outids"])           # bit-exact indices / order
+    assert np.array_equal(pairs, g["indice_pairs"])      # bit-exact rulebook
+    assert np.array_equal(num, g["indice_num"])
+    w = g["weight"].reshape(-1, g["weight"].shape[-2], g["weight"].shape[-1])
+    out32 = oracle.indice_conv(g["features"], w, pairs, num, outids.shape[0], False,
+                               bool(g["subm"]), acc64=False)
+    out64 = oracle.indice_conv(g["features"], w, pairs, num, outids.shape[0], False,
+                               bool(g["subm"]), acc64=True)
+    scale = np.abs(g["out"]).max()
+    assert np.abs(out32 - g["out"]).max() <= 1e-5 * scale
+    assert np.abs(out64 - g["out"]).max() <= 1e-5 * scale
+
+
+def test_bev_pool_matches_reference_quickcumsum(golden_dir):
+    g = np.load(os.path.join(golden_dir, "bev_pool_quickcumsum.npz"))
+    B, D, H, W = (int(v) for v in g["dims"])
+    feats, coords = g["feats"], g["coords"]
+    ranks = oracle.ranks_of(coords, B, D, H, W)
+    order, rs, starts, lengths = oracle.sort_and_intervals(ranks)
+    # the restated QuickCumsum reproduces the reference's own CPU path up to the fp32
+    # cumsum association order (torch scans blockwise, numpy serially; cancellation ~1e-4)
+    qc = oracle.quick_cumsum(feats[order], rs)
+    assert qc.shape == g["pooled"].shape
+    assert np.abs(qc - g["pooled"]).max() < 5e-4
+    assert np.array_equal(coords[order][starts + lengths - 1], g["pooled_geom"])
+    # gold (float64 interval sums) agrees with the reference within QuickCumsum's own
+    # cancellation error
+    out = oracle.bev_pool_forward(feats[order], coords[order].astype(np.int32), lengths, starts,
+                                  B, D, H, W, acc64=True)
+    cs = coords[order][starts]
+    got = out[cs[:, 3], cs[:, 2], cs[:, 0], cs[:, 1]]
+    assert np.abs(got - g["pooled"]).max() < 5e-4
+    # and the full op output has zeros exactly where no interval lands
+    mask = np.zeros((B, D, H, W), dtype=bool)
+    mask[cs[:, 3], cs[:, 2], cs[:, 0], cs[:, 1]] = True
+    assert np.all(out[~mask] == 0)
+
+
+def test_quantize_matches_torch_expression():
+    """base.py:149 in torch (fp32 sub, div, .long()) == oracle.quantize_filter."""
+    import torch
+    rng = np.random.default_rng(5)
+    geom = rng.uniform(-60, 60, size=(20000, 3)).astype(np.float32)
+    geom[:50] = np.array([[-54.0, 54.0, -10.0]], dtype=np.float32)    # on the boundaries
+    geom[50:100] = np.array([[-54.0 - 1e-4, 1.0, 0.0]], dtype=np.float32)  # x in (-1, 0) -> truncates to 0: kept
+    dx, bx, nx = oracle.gen_dx_bx([-54.0, 54.0, 0.3], [-54.0, 54.0, 0.3], [-10.0, 10.0, 20.0])
+    coords, kept = oracle.quantize_filter(geom, dx, bx, nx, 1)
+    tdx, tbx = torch.from_numpy(dx), torch.from_numpy(bx)
+    t = ((torch.from_numpy(geom) - (tbx - tdx / 2.0)) / tdx).long().numpy()
+    assert np.array_equal(coords[:, :3], t)
+    assert kept[50:100].all() and (coords[50:100, 0] == 0).all()
+
+
+def test_hard_voxelize_edge_cases():
+    vs, cr = [0.5, 0.5, 0.5], [0, 0, 0, 4, 4, 2]          # non-cubic grid (8, 8, 4)
+    # empty cloud
+    v, c, n, m = oracle.hard_voxelize(np.zeros((0, 4), np.float32), vs, cr, 3, 10)
+    assert m == 0 and v.shape == (0, 3, 4)
+    # all points out of range
+    pts = np.full((17, 4), 100.0, np.float32)
+    assert oracle.hard_voxelize(pts, vs, cr, 3, 10)[3] == 0
+    # all points in one voxel: one voxel, max_points kept, in index order
+    pts = np.tile(np.array([[0.1, 0.1, 0.1, 0.0]], np.float32), (9, 1))
+    pts[:, 3] = np.arange(9)
+    v, c, n, m = oracle.hard_voxelize(pts, vs, cr, 3, 10)
+    assert m == 1 and n[0] == 3 and list(v[0, :, 3]) == [0.0, 1.0, 2.0]
+    # max_voxels cap: later voxels dropped, later points of kept voxels still land
+    pts = np.array([[0.1, 0.1, 0.1, 0], [0.6, 0.1, 0.1, 1], [1.1, 0.1, 0.1, 2], [0.1, 0.1, 0.1, 3]],
+                   np.float32)
+    v, c, n, m = oracle.hard_voxelize(pts, vs, cr, 3, 2)
+    assert m == 2 and list(n) == [2, 1] and c.tolist() == [[0, 0, 0], [1, 0, 0]]

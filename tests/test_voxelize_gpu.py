@@ -1,0 +1,115 @@
+"""GPU parity tests for hard / dynamic voxelization.  Everything here is bit-exact
+(integer / byte work: coords, counts, order, point payloads)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from conftest import ref_module
+
+pytestmark = pytest.mark.gpu
+
+
+def run_ours(cuda, pts, vs, cr, mp, mv):
+    from bevfusion_b200.voxelize import voxelization
+    v, c, n = voxelization(torch.from_numpy(pts).to(cuda), list(vs), list(cr), mp, mv, True)
+    return v.cpu().numpy(), c.cpu().numpy(), n.cpu().numpy()
+
+
+def assert_same(ours, gold):
+    v, c, n = ours
+    gv, gc, gn, gm = gold
+    assert c.shape[0] == gm
+    assert np.array_equal(c, gc), "voxel coords / order differ"
+    assert np.array_equal(n, gn), "points-per-voxel differ"
+    assert np.array_equal(v, gv), "voxel payloads differ"
+
+
+@pytest.mark.parametrize("name", ["a", "b", "c"])
+def test_golden_fixture(cuda, golden_dir, name):
+    g = np.load(os.path.join(golden_dir, "voxelize_%s.npz" % name))
+    ours = run_ours(cuda, g["points"], g["voxel_size"], g["coors_range"], int(g["max_points"]),
+                    int(g["max_voxels"]))
+    assert_same(ours, (g["voxels"], g["coors"], g["num_points"], int(g["voxel_num"])))
+
+
+@pytest.mark.parametrize("n,mp,mv", [(1, 10, 5), (31, 2, 7), (4097, 10, 100000), (100000, 3, 3000)])
+def test_random_noncubic_vs_oracle(cuda, n, mp, mv):
+    from bevfusion_b200 import synthetic as S
+    vs, cr = [0.4, 0.5, 0.25], [-8.0, -6.0, -1.0, 8.0, 6.0, 3.0]     # grid 40 x 24 x 16
+    pts = S.uniform_cloud(n, seed=n, margin=1.0, rng_range=cr)
+    assert_same(run_ours(cuda, pts, vs, cr, mp, mv), oracle.hard_voxelize(pts, vs, cr, mp, mv))
+
+
+@pytest.mark.parametrize("shuffle", [True, False])
+@pytest.mark.parametrize("max_voxels", [120000, 160000])
+def test_full_size_c3(cuda, shuffle, max_voxels):
+    """BASELINE config C3: ~296 k points, 0.075 m voxels, grid 1440x1440x40; both caps bind."""
+    from bevfusion_b200 import synthetic as S
+    pts = S.lidar_cloud(seed=0, shuffle=shuffle)
+    L = S.LIDAR_C3
+    gold = oracle.hard_voxelize(pts, L["voxel_size"], L["point_cloud_range"], 10, max_voxels)
+    assert gold[3] == max_voxels                    # the synthetic cloud overflows the cap
+    assert (gold[2] == 10).any()                    # and max_points binds
+    assert_same(run_ours(cuda, pts, L["voxel_size"], L["point_cloud_range"], 10, max_voxels), gold)
+
+
+def test_edge_cases(cuda):
+    vs, cr = [0.5, 0.5, 0.5], [0, 0, 0, 4, 4, 2]
+    v, c, n = run_ours(cuda, np.zeros((0, 4), np.float32), vs, cr, 3, 10)
+    assert v.shape == (0, 3, 4) and c.shape == (0, 3) and n.shape == (0,)
+    assert run_ours(cuda, np.full((100, 4), 100.0, np.float32), vs, cr, 3, 10)[1].shape[0] == 0
+    # every point in ONE voxel (worst case for contention): first max_points indices survive
+    pts = np.tile(np.array([[0.1, 0.1, 0.1, 0.0]], np.float32), (20000, 1))
+    pts[:, 3] = np.arange(20000)
+    assert_same(run_ours(cuda, pts, vs, cr, 7, 10), oracle.hard_voxelize(pts, vs, cr, 7, 10))
+    # NaN / inf coordinates are dropped like out-of-range points
+    pts = np.array([[0.1, 0.1, 0.1, 1], [np.nan, 0.1, 0.1, 2], [0.1, np.inf, 0.1, 3], [0.2, 0.2, 0.2, 4]],
+                   np.float32)
+    v, c, n = run_ours(cuda, pts, vs, cr, 3, 10)
+    assert c.tolist() == [[0, 0, 0]] and n.tolist() == [2]
+
+
+def test_dynamic_voxelize(cuda):
+    from bevfusion_b200 import synthetic as S
+    from bevfusion_b200.voxelize import voxelization
+    vs, cr = [0.4, 0.5, 0.25], [-8.0, -6.0, -1.0, 8.0, 6.0, 3.0]
+    pts = S.uniform_cloud(50000, seed=9, margin=1.0, rng_range=cr)
+    coors = voxelization(torch.from_numpy(pts).to(cuda), vs, cr, -1, -1, True).cpu().numpy()
+    assert np.array_equal(coors, oracle.dynamic_voxelize(pts, vs, cr))
+
+
+def test_voxel_mean(cuda):
+    from bevfusion_b200 import synthetic as S
+    from bevfusion_b200.voxelize import voxelization, voxelize_mean
+    vs, cr = [0.4, 0.5, 0.25], [-8.0, -6.0, -1.0, 8.0, 6.0, 3.0]
+    pts = S.uniform_cloud(60000, seed=4, margin=0.5, rng_range=cr)
+    v, c, n = voxelization(torch.from_numpy(pts).to(cuda), vs, cr, 10, 20000, True)
+    feats, coords4 = voxelize_mean(v, c, n, batch_idx=3)
+    gold = oracle.voxel_mean(v.cpu().numpy(), n.cpu().numpy())
+    assert np.abs(feats.cpu().numpy() - gold).max() <= 1e-5 * np.abs(gold).max()
+    assert torch.equal(coords4[:, 1:], c) and int(coords4[:, 0].min()) == 3 == int(coords4[:, 0].max())
+    # and against the reference's torch expression (bevfusion.py:191-195)
+    ref = v.sum(dim=1) / n.type_as(v).view(-1, 1)
+    assert float((feats - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
+
+
+def test_vs_reference_cuda_kernel(cuda):
+    """the reference's deterministic GPU voxelizer (O(N^2) + serial kernel), compiled unmodified."""
+    ref = ref_module("voxel_layer_ref")
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    from bevfusion_b200 import synthetic as S
+    L = S.LIDAR_C3
+    pts = S.lidar_cloud(seed=1, sweeps=2)            # ~59 k points keeps the O(N^2) scan short
+    p = torch.from_numpy(pts).to(cuda)
+    mp, mv = 10, 20000
+    voxels = torch.zeros(mv, mp, 5, device=cuda)
+    coors = torch.zeros(mv, 3, dtype=torch.int32, device=cuda)
+    num = torch.zeros(mv, dtype=torch.int32, device=cuda)
+    m = ref.hard_voxelize(p, voxels, coors, num, L["voxel_size"], L["point_cloud_range"], mp, mv, 3, True)
+    assert m == mv
+    ours = run_ours(cuda, pts, L["voxel_size"], L["point_cloud_range"], mp, mv)
+    assert_same(ours, (voxels[:m].cpu().numpy(), coors[:m].cpu().numpy(), num[:m].cpu().numpy(), m))
