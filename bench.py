@@ -302,7 +302,7 @@ def run_ours(args, rank, world, local_rank):
         "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": 1, "parallelism": "sample-parallel x%d" % world,
-                   "spconv_precision": {None: "env/default fp32", 0: "fp32", 1: "tf32x3", 2: "tf32"}[args.precision],
+                   "spconv_precision": {None: "tf32x3 (tcgen05, 3xTF32 split; default)", 0: "fp32 (SIMT)", 1: "tf32x3", 2: "tf32"}[args.precision],
                    "l2": "inputs larger than L2: the 638 MB feature volume streams through L2 every step",
                    "bev_pool_plan": "rank/sort/interval tables cached per calibration (static geometry)",
                    "kept_rows": hp.n_kept, "intervals": hp.n_intervals},

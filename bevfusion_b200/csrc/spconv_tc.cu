@@ -123,13 +123,14 @@ struct TcParams {
   const float *scale, *shift, *residual;
   float *out;
   int n_in, n_out, c_in, c_out, kvol, relu;
-  int nkb;        // K blocks per offset = ceil(c_in / 32)
+  int nkb;        // K blocks of 32 floats over the concatenated (offset, channel) axis
+  int cin_shift;  // log2(c_in): c_in is a power of two >= 16 on this path
   int nstages;
   int tmem_cols;  // power of two >= max(32, c_out)
 };
 
 template <int NSPLIT>
-__global__ void __launch_bounds__(kTcThreads, 1) spconv_tc_kernel(const TcParams p) {
+__global__ void __launch_bounds__(kTcThreads, 2) spconv_tc_kernel(const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // align the stage area to 1024 B (SWIZZLE_128B atoms)
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -161,60 +162,84 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_tc_kernel(const TcParams
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
-  const int n_iters = p.kvol * p.nkb;
+  const int n_iters = p.nkb;
 
   if (warp < 8) {
     // =============================== producers ===========================================
     const int r = tid & 127, half = tid >> 7;
-    const int o = row0 + r;
     const uint32_t sw = (uint32_t)(r & 7);
     const uint32_t row_off = (uint32_t)r * 128u;
-    int it = 0;
-    for (int k = 0; k < p.kvol; ++k) {
-      int src = o < p.n_out ? __ldg(p.nbr + (long long)k * p.n_out + o) : -1;
-      if (src >= p.n_in) src = -1;
-      const float4 *frow = reinterpret_cast<const float4 *>(p.features + (long long)max(src, 0) * p.c_in);
-      for (int kb = 0; kb < p.nkb; ++kb, ++it) {
-        const int s = it % NS;
-        const uint32_t ph = (uint32_t)(it / NS) & 1u;
-        // global loads first (independent of the smem slot), then wait for the slot
-        float4 v[4];
+    // neighbour rows of this tile for every offset, staged once in shared memory
+    int32_t *nbr_s = reinterpret_cast<int32_t *>(smem + (size_t)NS * stage_bytes);
+    for (int i = tid; i < p.kvol * kTileM; i += kTcProducerThreads) {
+      const int k = i >> 7, rr = i & 127, o = row0 + rr;
+      int v = o < p.n_out ? __ldg(p.nbr + (long long)k * p.n_out + o) : -1;
+      if (v >= p.n_in) v = -1;
+      nbr_s[i] = v;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kTcProducerThreads) : "memory");
+
+    // K block `it` covers concatenated-K indices [32*it, 32*it+32); this thread owns 16 of them
+    // (4 float4 chunks), which lie inside ONE kernel offset because c_in % 16 == 0.
+    auto issue = [&](int it, float4 (&v)[4]) {
+      const int kk = it * kKBlock + half * 16;
+      const int k = kk >> p.cin_shift;
+      const int ch = kk & (p.c_in - 1);
+      const int src = k < p.kvol ? nbr_s[k * kTileM + r] : -1;
+      if (src >= 0) {
+        const float4 *q = reinterpret_cast<const float4 *>(p.features + (long long)src * p.c_in + ch);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          int c4 = kb * 8 + half * 4 + j;  // float4 index inside the feature row
-          v[j] = (src >= 0 && c4 * 4 < p.c_in) ? __ldg(frow + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        mbar_wait(empty0 + 8 * s, ph ^ 1u);
-        const uint32_t stage = smem_base + (uint32_t)s * (uint32_t)stage_bytes;
-        if (tid == 0) {
-          const uint32_t bbytes = (uint32_t)(NSPLIT * b_part_bytes);
-          mbar_arrive_expect_tx(full0 + 8 * s, bbytes);
-          const float *wsrc = p.wpacked + ((long long)k * p.nkb + kb) * (long long)(NSPLIT * p.c_out * 32);
-          bulk_copy_g2s(stage + NSPLIT * kABlockBytes, wsrc, bbytes, full0 + 8 * s);
-        }
+        for (int j = 0; j < 4; ++j) v[j] = __ldg(q + j);
+      } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t chunk = (uint32_t)(half * 4 + j);
-          const uint32_t off = row_off + ((chunk ^ sw) << 4);
-          uint4 hi;
-          hi.x = __float_as_uint(v[j].x) & 0xffffe000u;
-          hi.y = __float_as_uint(v[j].y) & 0xffffe000u;
-          hi.z = __float_as_uint(v[j].z) & 0xffffe000u;
-          hi.w = __float_as_uint(v[j].w) & 0xffffe000u;
-          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(stage + off), "r"(hi.x), "r"(hi.y),
-                       "r"(hi.z), "r"(hi.w) : "memory");
-          if (NSPLIT == 2) {
-            float4 lo;
-            lo.x = v[j].x - __uint_as_float(hi.x);
-            lo.y = v[j].y - __uint_as_float(hi.y);
-            lo.z = v[j].z - __uint_as_float(hi.z);
-            lo.w = v[j].w - __uint_as_float(hi.w);
-            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stage + kABlockBytes + off),
-                         "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
+        for (int j = 0; j < 4; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    constexpr int PD = 4;  // register prefetch distance (K blocks in flight per thread)
+    float4 v[PD][4];
+#pragma unroll
+    for (int j = 0; j < PD; ++j)
+      if (j < n_iters) issue(j, v[j]);
+    for (int it0 = 0; it0 < n_iters; it0 += PD) {
+#pragma unroll
+      for (int jj = 0; jj < PD; ++jj) {
+        const int it = it0 + jj;
+        if (it < n_iters) {
+          const int s = it % NS;
+          const uint32_t ph = (uint32_t)(it / NS) & 1u;
+          mbar_wait(empty0 + 8 * s, ph ^ 1u);
+          const uint32_t stage = smem_base + (uint32_t)s * (uint32_t)stage_bytes;
+          if (tid == 0) {
+            const uint32_t bbytes = (uint32_t)(NSPLIT * b_part_bytes);
+            mbar_arrive_expect_tx(full0 + 8 * s, bbytes);
+            const float *wsrc = p.wpacked + (long long)it * (long long)(NSPLIT * p.c_out * 32);
+            bulk_copy_g2s(stage + NSPLIT * kABlockBytes, wsrc, bbytes, full0 + 8 * s);
           }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t chunk = (uint32_t)(half * 4 + j);
+            const uint32_t off = row_off + ((chunk ^ sw) << 4);
+            uint4 hi;
+            hi.x = __float_as_uint(v[jj][j].x) & 0xffffe000u;
+            hi.y = __float_as_uint(v[jj][j].y) & 0xffffe000u;
+            hi.z = __float_as_uint(v[jj][j].z) & 0xffffe000u;
+            hi.w = __float_as_uint(v[jj][j].w) & 0xffffe000u;
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(stage + off), "r"(hi.x), "r"(hi.y),
+                         "r"(hi.z), "r"(hi.w) : "memory");
+            if (NSPLIT == 2) {
+              float4 lo;
+              lo.x = v[jj][j].x - __uint_as_float(hi.x);
+              lo.y = v[jj][j].y - __uint_as_float(hi.y);
+              lo.z = v[jj][j].z - __uint_as_float(hi.z);
+              lo.w = v[jj][j].w - __uint_as_float(hi.w);
+              asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stage + kABlockBytes + off),
+                           "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
+            }
+          }
+          fence_proxy_async();           // generic-proxy stores -> visible to the tensor core (async proxy)
+          mbar_arrive(full0 + 8 * s);
+          if (it + PD < n_iters) issue(it + PD, v[jj]);
         }
-        fence_proxy_async();           // generic-proxy stores -> visible to the tensor core (async proxy)
-        mbar_arrive(full0 + 8 * s);
       }
     }
     // =============================== epilogue ============================================
@@ -261,7 +286,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_tc_kernel(const TcParams
     for (int it = 0; it < n_iters; ++it) {
       const int s = it % NS;
       const uint32_t ph = (uint32_t)(it / NS) & 1u;
-      const int kb = it % p.nkb;
       mbar_wait(full0 + 8 * s, ph);
       tc_fence_after();
       if (lane == 0) {
@@ -270,8 +294,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_tc_kernel(const TcParams
         const uint64_t a_lo = umma_desc_sw128(stage + kABlockBytes);
         const uint64_t b_hi = umma_desc_sw128(stage + NSPLIT * kABlockBytes);
         const uint64_t b_lo = umma_desc_sw128(stage + NSPLIT * kABlockBytes + b_part_bytes);
-        const int ksteps = min(4, (p.c_in - kb * kKBlock + 7) / 8);
-        for (int ks = 0; ks < ksteps; ++ks) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
           const uint64_t adv = (uint64_t)(ks * 2);  // +32 B along K inside the 128-byte swizzle row
           if (NSPLIT == 2) {
             // small terms first, then the dominant product
@@ -297,22 +321,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_tc_kernel(const TcParams
   }
 }
 
-// weight [K][Cin][Cout] fp32 -> packed [K][nkb][nsplit][Cout][32] in the swizzled smem image:
-// element (n, c) of a K block sits at float index n*32 + (((c/4) ^ (n&7)) * 4) + (c%4)
+// weight [K][Cin][Cout] fp32 -> packed [nkb][nsplit][Cout][32] in the swizzled smem image.  The K
+// axis is the concatenation over kernel offsets of the Cin channels (kk = k*Cin + ci), cut into
+// blocks of 32; element (n, c) of block kb sits at float index n*32 + (((c/4) ^ (n&7)) * 4) + (c%4).
 __global__ void spconv_pack_weights_kernel(const float *__restrict__ w, int kvol, int c_in, int c_out,
                                            int nkb, int nsplit, float *__restrict__ packed) {
-  const long long total = (long long)kvol * nkb * c_out * 32;
+  const long long total = (long long)nkb * c_out * 32;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
        t += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(t % 32);
-    int n = (int)((t / 32) % c_out);
-    int kb = (int)((t / (32ll * c_out)) % nkb);
-    int k = (int)(t / (32ll * c_out * nkb));
-    int ci = kb * 32 + c;
-    float v = ci < c_in ? w[((long long)k * c_in + ci) * c_out + n] : 0.f;
-    float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
-    long long blk = ((long long)k * nkb + kb) * nsplit;
-    int pos = n * 32 + ((((c >> 2) ^ (n & 7)) << 2) | (c & 3));
+    const int c = (int)(t % 32);
+    const int n = (int)((t / 32) % c_out);
+    const int kb = (int)(t / (32ll * c_out));
+    const int kk = kb * 32 + c;
+    const int k = kk / c_in, ci = kk % c_in;
+    const float v = k < kvol ? w[((long long)k * c_in + ci) * c_out + n] : 0.f;
+    const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    const long long blk = (long long)kb * nsplit;
+    const int pos = n * 32 + ((((c >> 2) ^ (n & 7)) << 2) | (c & 3));
     packed[(blk + 0) * c_out * 32 + pos] = hi;
     if (nsplit == 2) packed[(blk + 1) * c_out * 32 + pos] = v - hi;
   }
@@ -323,16 +348,41 @@ int spconv_forward_simt(const float *features, const float *weight, const int32_
                         const float *shift, const float *residual, int relu, float *out,
                         cudaStream_t st);
 
-int spconv_forward_tc(const float *features, const float *weight, const int32_t *nbr, int n_in,
-                      int n_out, int c_in, int c_out, int kvol, const float *scale,
-                      const float *shift, const float *residual, int relu, int precision,
-                      float *out, cudaStream_t st) {
-  const bool shape_ok = (c_out == 16 || c_out == 32 || c_out == 64 || c_out == 128) &&
-                        (c_in % 8 == 0) && c_in >= 8 && c_in <= 512 &&
-                        ((uintptr_t)features % 16 == 0) && ((uintptr_t)out % 16 == 0) &&
-                        (residual == nullptr || (uintptr_t)residual % 16 == 0);
-  if (!shape_ok) {
+static bool tc_shape_ok(int c_in, int c_out, int kvol) {
+  return (c_out == 16 || c_out == 32 || c_out == 64 || c_out == 128) &&
+         (c_in == 16 || c_in == 32 || c_in == 64 || c_in == 128) && kvol >= 1 && kvol <= 27;
+}
+
+static int tc_nkb(int c_in, int kvol) { return (kvol * c_in + kKBlock - 1) / kKBlock; }
+
+size_t spconv_packed_bytes(int c_in, int c_out, int kvol, int precision) {
+  if (!tc_shape_ok(c_in, c_out, kvol)) return 0;
+  const int nsplit = precision == BEVB200_PREC_TF32X3 ? 2 : 1;
+  return (size_t)tc_nkb(c_in, kvol) * nsplit * c_out * 32 * sizeof(float);
+}
+
+int spconv_pack_weights(const float *weight, int c_in, int c_out, int kvol, int precision,
+                        float *packed, cudaStream_t st) {
+  const int nsplit = precision == BEVB200_PREC_TF32X3 ? 2 : 1;
+  const int nkb = tc_nkb(c_in, kvol);
+  BEVB200_LAUNCH(spconv_pack_weights_kernel, grid_for((long long)nkb * c_out * 32, 256), 256, 0, st,
+                 weight, kvol, c_in, c_out, nkb, nsplit, packed);
+  return BEVB200_OK;
+}
+
+// `packed` may be null: the weights are then packed into a stream-ordered temporary.
+int spconv_forward_tc(const float *features, const float *weight, const float *packed_in,
+                      const int32_t *nbr, int n_in, int n_out, int c_in, int c_out, int kvol,
+                      const float *scale, const float *shift, const float *residual, int relu,
+                      int precision, float *out, cudaStream_t st) {
+  const bool ok = tc_shape_ok(c_in, c_out, kvol) && ((uintptr_t)features % 16 == 0) &&
+                  ((uintptr_t)out % 16 == 0) && (residual == nullptr || (uintptr_t)residual % 16 == 0);
+  if (!ok) {
     // shapes the UMMA tile cannot take (e.g. conv_input, Cin = 5): exact-fp32 SIMT kernel
+    if (weight == nullptr) {
+      snprintf(g_last_error, sizeof(g_last_error), "spconv_forward: shape needs the unpacked weights");
+      return BEVB200_EINVAL;
+    }
     return spconv_forward_simt(features, weight, nbr, n_in, n_out, c_in, c_out, kvol, scale, shift,
                                residual, relu, out, st);
   }
@@ -341,21 +391,30 @@ int spconv_forward_tc(const float *features, const float *weight, const int32_t 
   p.features = features; p.nbr = nbr; p.scale = scale; p.shift = shift; p.residual = residual;
   p.out = out; p.n_in = n_in; p.n_out = n_out; p.c_in = c_in; p.c_out = c_out; p.kvol = kvol;
   p.relu = relu;
-  p.nkb = (c_in + kKBlock - 1) / kKBlock;
+  p.nkb = tc_nkb(c_in, kvol);
+  p.cin_shift = 0;
+  while ((1 << p.cin_shift) < c_in) ++p.cin_shift;
   p.tmem_cols = c_out < 32 ? 32 : c_out;
   const int stage_bytes = nsplit * (kABlockBytes + c_out * 128);
-  int ns = (200 * 1024) / stage_bytes;
-  if (ns > 6) ns = 6;
-  if (ns < 2) ns = 2;
+  // two CTAs per SM when the stages are small enough (overlaps one tile's epilogue with the
+  // other's main loop); otherwise one CTA with a deeper ring
+  const int nbr_bytes = kvol * kTileM * 4;
+  int ns = 2;
+  if (2 * stage_bytes + nbr_bytes + 1024 > 111 * 1024) {
+    ns = (215 * 1024 - nbr_bytes) / stage_bytes;
+    if (ns > 4) ns = 4;
+  }
   p.nstages = ns;
-  const size_t smem = (size_t)ns * stage_bytes + 1024;
-  // packed weights: stream-ordered temporary (weights are tiny: <= 3.5 MB)
+  const size_t smem = (size_t)ns * stage_bytes + nbr_bytes + 1024;
   float *packed = nullptr;
-  const size_t packed_bytes = (size_t)kvol * p.nkb * nsplit * c_out * 32 * sizeof(float);
-  BEVB200_CUDA(cudaMallocAsync((void **)&packed, packed_bytes, st));
-  BEVB200_LAUNCH(spconv_pack_weights_kernel, grid_for((long long)kvol * p.nkb * c_out * 32, 256), 256,
-                 0, st, weight, kvol, c_in, c_out, p.nkb, nsplit, packed);
-  p.wpacked = packed;
+  if (packed_in == nullptr) {
+    BEVB200_CUDA(cudaMallocAsync((void **)&packed, spconv_packed_bytes(c_in, c_out, kvol, precision), st));
+    int rc = spconv_pack_weights(weight, c_in, c_out, kvol, precision, packed, st);
+    if (rc) return rc;
+    p.wpacked = packed;
+  } else {
+    p.wpacked = packed_in;
+  }
   const int grid = (n_out + kTileM - 1) / kTileM;
   if (nsplit == 2) {
     BEVB200_CUDA(cudaFuncSetAttribute(spconv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -366,7 +425,7 @@ int spconv_forward_tc(const float *features, const float *weight, const int32_t 
                                       (int)smem));
     BEVB200_LAUNCH(spconv_tc_kernel<1>, grid, kTcThreads, smem, st, p);
   }
-  BEVB200_CUDA(cudaFreeAsync(packed, st));
+  if (packed) BEVB200_CUDA(cudaFreeAsync(packed, st));
   return BEVB200_OK;
 }
 

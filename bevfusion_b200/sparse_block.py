@@ -31,7 +31,19 @@ def build_norm_layer(cfg, num_features, postfix=""):
 
 
 def bn_scale_shift(bn):
-    """Fold an eval-mode BatchNorm1d into per-channel (scale, shift)."""
+    """Fold an eval-mode BatchNorm1d into per-channel (scale, shift); cached on the module until
+    one of its parameters / buffers changes."""
+    tensors = [t for t in (bn.weight, bn.bias, bn.running_mean, bn.running_var) if t is not None]
+    key = tuple((t.data_ptr(), t._version) for t in tensors)
+    cached = getattr(bn, "_b200_fold", None)
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    out = _bn_scale_shift(bn)
+    bn._b200_fold = (key, out)
+    return out
+
+
+def _bn_scale_shift(bn):
     scale = (bn.weight.detach() if bn.affine else torch.ones_like(bn.running_mean)) \
         * torch.rsqrt(bn.running_var + bn.eps)
     shift = (bn.bias.detach() if bn.affine else torch.zeros_like(bn.running_mean)) \

@@ -79,7 +79,20 @@ class SparseConvolution(SparseModule):
             self.bias = Parameter(torch.Tensor(out_channels))
         else:
             self.register_parameter("bias", None)
+        self._packed_cache = None
         self.reset_parameters()
+
+    def _packed_weight(self, precision):
+        """tensor-core image of the weights, rebuilt only when the parameter changes"""
+        if precision is None:
+            precision = ops.default_precision()
+        if precision == ops.PREC_FP32:
+            return None
+        w = self.weight
+        key = (int(precision), w.data_ptr(), w._version, str(w.device))
+        if self._packed_cache is None or self._packed_cache[0] != key:
+            self._packed_cache = (key, ops.pack_weights(w.detach().contiguous(), precision))
+        return self._packed_cache[1]
 
     def reset_parameters(self):
         init.kaiming_uniform_(self.weight, a=math.sqrt(5))
@@ -139,7 +152,8 @@ class SparseConvolution(SparseModule):
                 shift = b * scale + shift if scale is not None and shift is not None else (
                     b * scale if scale is not None else (b + shift if shift is not None else b))
             out_features = ops.sparse_conv(features.contiguous(), self.weight.detach().contiguous(),
-                                           rb.nbr, rb.n_out, scale, shift, residual, relu, precision)
+                                           rb.nbr, rb.n_out, scale, shift, residual, relu, precision,
+                                           packed=self._packed_weight(precision))
         else:
             fn = Fsp.indice_subm_conv if self.subm else Fsp.indice_conv
             out_features = fn(features, self.weight, rb, None, rb.n_out)

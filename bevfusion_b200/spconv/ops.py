@@ -23,7 +23,7 @@ _PREC_NAMES = {"fp32": PREC_FP32, "tf32x3": PREC_TF32X3, "tf32": PREC_TF32}
 
 def default_precision():
     """Precision of the sparse-conv GEMMs: env BEVB200_SPCONV_PRECISION in {fp32, tf32x3, tf32}."""
-    return _PREC_NAMES[os.environ.get("BEVB200_SPCONV_PRECISION", "fp32").lower()]
+    return _PREC_NAMES[os.environ.get("BEVB200_SPCONV_PRECISION", "tf32x3").lower()]
 
 
 def get_conv_output_size(input_size, kernel_size, stride, padding, dilation):
@@ -156,9 +156,30 @@ def nbr_from_pairs(indice_pairs, indice_pair_num, num_activate_out, inverse=Fals
     return nbr
 
 
+def pack_weights(weight, precision=None):
+    """Pre-pack conv weights [k..., Cin, Cout] for the tensor-core kernel (None when the shape /
+    precision has no tensor-core form).  Do this once for static weights."""
+    _C.require_cuda(weight, "weight", torch.float32)
+    if precision is None:
+        precision = default_precision()
+    c_in, c_out = weight.shape[-2], weight.shape[-1]
+    kvol = weight.numel() // (c_in * c_out)
+    nbytes = _C.lib().bevb200_spconv_packed_weight_bytes(c_in, c_out, kvol, int(precision))
+    if nbytes == 0:
+        return None
+    dev = weight.device
+    with torch.cuda.device(dev):
+        packed = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
+        rc = _C.lib().bevb200_spconv_pack_weights(_C.ptr(weight), c_in, c_out, kvol, int(precision),
+                                                  _C.ptr(packed), _C.current_stream(dev))
+    _C.check(rc, "spconv_pack_weights")
+    return packed
+
+
 def sparse_conv(features, weight, nbr, n_out, scale=None, shift=None, residual=None, relu=False,
-                precision=None):
-    """out[o] = epilogue(sum_k features[nbr[k, o]] @ weight[k]) -- one implicit-GEMM launch."""
+                precision=None, packed=None):
+    """out[o] = epilogue(sum_k features[nbr[k, o]] @ weight[k]) -- one implicit-GEMM launch.
+    `packed` = pack_weights(weight, precision) skips the per-call weight packing."""
     _C.require_cuda(features, "features", torch.float32)
     _C.require_cuda(weight, "weight", torch.float32)
     _C.require_cuda(nbr, "nbr", torch.int32)
@@ -179,10 +200,16 @@ def sparse_conv(features, weight, nbr, n_out, scale=None, shift=None, residual=N
     dev = features.device
     with torch.cuda.device(dev):
         out = torch.empty((n_out, c_out), dtype=torch.float32, device=dev)
-        rc = _C.lib().bevb200_spconv_forward(
-            _C.ptr(features), _C.ptr(weight), _C.ptr(nbr), n_in, int(n_out), c_in, c_out, kvol,
-            _C.ptr(scale), _C.ptr(shift), _C.ptr(residual), int(bool(relu)), int(precision),
-            _C.ptr(out), _C.current_stream(dev))
+        if packed is not None and precision != PREC_FP32:
+            rc = _C.lib().bevb200_spconv_forward_packed(
+                _C.ptr(features), _C.ptr(packed), _C.ptr(nbr), n_in, int(n_out), c_in, c_out, kvol,
+                _C.ptr(scale), _C.ptr(shift), _C.ptr(residual), int(bool(relu)), int(precision),
+                _C.ptr(out), _C.current_stream(dev))
+        else:
+            rc = _C.lib().bevb200_spconv_forward(
+                _C.ptr(features), _C.ptr(weight), _C.ptr(nbr), n_in, int(n_out), c_in, c_out, kvol,
+                _C.ptr(scale), _C.ptr(shift), _C.ptr(residual), int(bool(relu)), int(precision),
+                _C.ptr(out), _C.current_stream(dev))
     _C.check(rc, "spconv_forward")
     return out
 

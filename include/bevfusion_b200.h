@@ -239,6 +239,23 @@ BEVB200_API int bevb200_spconv_forward(const float *features, const float *weigh
                            const float *scale, const float *shift, const float *residual,
                            int relu, int precision, float *out, void *stream);
 
+/* Tensor-core path with pre-packed weights.  The tcgen05 kernel consumes the weights as a
+ * pre-swizzled shared-memory image (K blocks of 32 over the concatenated (offset, channel)
+ * axis, tf32 hi / lo parts); bevb200_spconv_forward() builds it into a stream-ordered temporary
+ * on every call, these entry points let a caller with static weights (eval mode) do it once.
+ * bevb200_spconv_packed_weight_bytes() returns 0 when (c_in, c_out, kernel_volume, precision)
+ * has no tensor-core form (c_in, c_out in {16,32,64,128}, kernel_volume <= 27, precision TF32X3
+ * or TF32); such shapes go through bevb200_spconv_forward(), which falls back to the fp32
+ * SIMT kernel on the GPU. */
+BEVB200_API size_t bevb200_spconv_packed_weight_bytes(int c_in, int c_out, int kernel_volume, int precision);
+BEVB200_API int bevb200_spconv_pack_weights(const float *weight, int c_in, int c_out, int kernel_volume,
+                                int precision, float *packed, void *stream);
+BEVB200_API int bevb200_spconv_forward_packed(const float *features, const float *packed_weight,
+                                  const int32_t *nbr, int n_in, int n_out, int c_in, int c_out,
+                                  int kernel_volume, const float *scale, const float *shift,
+                                  const float *residual, int relu, int precision, float *out,
+                                  void *stream);
+
 /* SparseConvTensor.dense() (structure.py:49-59) fused with SparseEncoder's
  * permute(0,1,4,2,3).view(N, C*D, H, W) (sparse_encoder.py:126-130):
  *   out[b, c*Z + z, x, y] = features[i, c] for indices[i] = (b, x, y, z); zero elsewhere.
