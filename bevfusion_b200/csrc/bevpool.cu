@@ -19,6 +19,8 @@
 //     map, which removes x[kept] / feats[indices] (2 x 0.6 GB of copies) from the frame
 #include <cub/device/device_radix_sort.cuh>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace bevb200 {
@@ -202,6 +204,267 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// forward, v2: TMA-staged streaming reduction (the default for the tuned channel widths)
+// ---------------------------------------------------------------------------------------
+// Every warp owns a contiguous range of the sorted row stream and runs its own
+// cp.async.bulk -> shared memory ring (32 rows per stage, mbarrier complete_tx), so the bytes in
+// flight per SM (warps x stages x 32 rows x C x 4 B, ~120-180 KB) do not depend on registers or
+// on the interval lengths.  Rows are gathered through `perm` with one 16*Q-byte bulk copy per
+// row (one copy of the whole stage when the rows are already sorted).  The warp then walks the
+// staged rows in order: lane q owns float4 column q, adds rows into a register accumulator and
+// flushes it at interval boundaries (bitmask per stage built from the interval table) with a
+// coalesced 16-byte-per-lane store.  An interval that crosses a warp-range boundary leaves its
+// pieces in `partial` (2 slots per range: head = continuation from the previous range, tail =
+// continues into the next) and the fix-up kernel adds them in range order: fixed summation
+// order, bit-reproducible, no float atomics.  Requires the intervals to tile [0, n) in order,
+// which is how QuickCumsumCuda (bev_pool.py:41-46) builds them; the host checks nothing else.
+constexpr int kStageRows = 32;
+constexpr int kPoolStages = 3;
+
+__device__ __forceinline__ uint32_t pool_smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void pool_mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "PW_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra PW_DONE;\n\t"
+      "bra PW_LOOP;\n\t"
+      "PW_DONE:\n\t}"
+      ::"r"(bar), "r"(parity) : "memory");
+}
+
+__global__ void pool_interval_cells_kernel(const int32_t *__restrict__ geom_feats,
+                                           const int32_t *__restrict__ starts, int n, int n_intervals,
+                                           PoolDims dm, int32_t *__restrict__ cells) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_intervals; i += gridDim.x * blockDim.x) {
+    int s = starts[i];
+    long long c = (s >= 0 && s < n) ? cell_of(geom_feats, s, dm) : -1;
+    cells[i] = (int32_t)c;  // host guarantees b*d*h*w < 2^31
+  }
+}
+
+template <int Q, bool PERM>
+__global__ void __launch_bounds__(256)
+    bevpool_fwd_tma_kernel(const float4 *__restrict__ x, const int32_t *__restrict__ perm,
+                           const int32_t *__restrict__ starts, const int32_t *__restrict__ cells,
+                           int n, int n_intervals, int rows_per_warp, int zfill, int total_cells,
+                           float4 *__restrict__ out, float4 *__restrict__ partial) {
+  constexpr int QPL = (Q + 31) / 32;              // float4 columns per lane
+  constexpr uint32_t kRowBytes = Q * 16;
+  constexpr uint32_t kStageBytes = kStageRows * kRowBytes;
+  extern __shared__ __align__(128) uint8_t pool_smem[];
+  __shared__ uint64_t bars[8 * kPoolStages];
+  const int warp = threadIdx.x >> 5, lane = lane_id(), nwarps = blockDim.x >> 5;
+  const int j = blockIdx.x * nwarps + warp;       // warp-range index
+  const long long R0l = (long long)j * rows_per_warp;
+  if (R0l >= n) return;
+  const int R0 = (int)R0l, R1 = min(n, R0 + rows_per_warp);
+  uint8_t *my = pool_smem + (size_t)warp * kPoolStages * kStageBytes;
+  const uint32_t my_u32 = pool_smem_u32(my);
+  const uint32_t bar0 = pool_smem_u32(&bars[warp * kPoolStages]);
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kPoolStages; ++s)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8 * s));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  const int n_stages = (R1 - R0 + kStageRows - 1) / kStageRows;
+
+  // Stage fill.  Sorted rows (PERM == false): ONE cp.async.bulk (TMA) of the whole stage,
+  // completion on the stage's mbarrier.  Gathered rows (PERM == true): per-row bulk copies are
+  // TMA-issue bound (measured: ~27 clk per 320-byte copy per SM), so the rows are gathered with
+  // 16-byte cp.async (LDGSTS, no registers held) -- lane l holds the source row of stage row l,
+  // float4 f of the stage comes from row f / Q -- and completion is tracked per commit group.
+  auto issue = [&](int it) {
+    const int s = it % kPoolStages;
+    const int r0s = R0 + it * kStageRows;
+    const int nrows = min(kStageRows, R1 - r0s);
+    const uint32_t dst = my_u32 + (uint32_t)s * kStageBytes;
+    if constexpr (PERM) {
+      const long long prow = lane < nrows ? (long long)__ldg(perm + r0s + lane) : 0ll;
+#pragma unroll
+      for (int t = 0; t < Q; ++t) {
+        const int f = lane + 32 * t;
+        const int row = f / Q, q = f - row * Q;
+        const long long srow = __shfl_sync(0xffffffffu, prow, row);
+        if (row < nrows)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)f * 16u),
+                       "l"(x + srow * Q + q) : "memory");
+      }
+    } else {
+      const uint32_t bar = bar0 + 8 * s;
+      if (lane == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
+                     "r"((uint32_t)nrows * kRowBytes) : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+            ::"r"(dst), "l"(x + (long long)r0s * Q), "r"((uint32_t)nrows * kRowBytes), "r"(bar) : "memory");
+      }
+    }
+  };
+  auto commit = [&]() {
+    if constexpr (PERM) asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  for (int it = 0; it < kPoolStages; ++it) {
+    if (it < n_stages) issue(it);
+    commit();                                     // one group per ring slot, even when empty
+  }
+
+  // interval bookkeeping: `ibase` = first interval whose start is >= the current stage's first row
+  float4 acc[QPL];
+#pragma unroll
+  for (int u = 0; u < QPL; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+  bool open = false, head = false;   // an interval is being accumulated / it began before R0
+  int cur_cell = -1;
+  int ibase;
+  {
+    int i0 = find_interval(starts, n_intervals, R0);
+    if (i0 >= 0 && __ldg(starts + i0) == R0) {
+      ibase = i0;
+    } else {
+      ibase = i0 + 1;
+      if (i0 >= 0) { open = true; head = true; }
+    }
+  }
+  auto flush = [&](bool final_piece_continues) {
+    if (!open) return;
+    float4 *dst;
+    if (head) dst = partial + (2ll * j) * Q;
+    else if (final_piece_continues) dst = partial + (2ll * j + 1) * Q;
+    else dst = cur_cell >= 0 ? out + (long long)cur_cell * Q : nullptr;
+    if (dst) {
+#pragma unroll
+      for (int u = 0; u < QPL; ++u) {
+        const int q = lane + 32 * u;
+        if (q < Q) dst[q] = acc[u];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < QPL; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    open = false; head = false;
+  };
+
+  // with `zfill` (cells ascend with the interval index: plan tables, B*D == 1) the warp that
+  // opens interval i also zeroes the empty cells between interval i-1 and i, so the grid needs
+  // no separate memset pass
+  auto zero_cells = [&](int lo, int hi) {        // cells [lo, hi)
+    const long long cnt = (long long)(hi - lo) * Q;
+    float4 *dst = out + (long long)lo * Q;
+    for (long long i = lane; i < cnt; i += 32) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  // interval table of the NEXT stage is fetched while the current one is reduced
+  int st_n = ibase + lane < n_intervals ? __ldg(starts + ibase + lane) : 0x7fffffff;
+  int cell_n = ibase + lane < n_intervals ? __ldg(cells + ibase + lane) : -1;
+  int pc_n = ibase > 0 ? __ldg(cells + ibase - 1) : -1;
+  for (int it = 0; it < n_stages; ++it) {
+    const int s = it % kPoolStages;
+    const int r0s = R0 + it * kStageRows;
+    const int nrows = min(kStageRows, R1 - r0s);
+    const int st = st_n, cellv = cell_n, prev_cell_base = pc_n;
+    const bool in_stage = st < r0s + nrows;      // st >= r0s by construction of ibase
+    const uint32_t mask = __reduce_or_sync(0xffffffffu, in_stage ? (1u << (st - r0s)) : 0u);
+    const int ib_cur = ibase;
+    ibase += __popc(mask);
+    if (it + 1 < n_stages) {
+      st_n = ibase + lane < n_intervals ? __ldg(starts + ibase + lane) : 0x7fffffff;
+      cell_n = ibase + lane < n_intervals ? __ldg(cells + ibase + lane) : -1;
+      pc_n = ibase > 0 ? __ldg(cells + ibase - 1) : -1;
+    }
+    if constexpr (PERM) {
+      asm volatile("cp.async.wait_group %0;" ::"n"(kPoolStages - 1) : "memory");
+      __syncwarp();                                // other lanes' copies are visible after their wait
+    } else {
+      pool_mbar_wait(bar0 + 8 * s, (uint32_t)(it / kPoolStages) & 1u);
+    }
+    const float4 *rows = reinterpret_cast<const float4 *>(my + (size_t)s * kStageBytes);
+    int row = 0, iv = 0;   // iv = how many boundaries of this stage have been consumed
+    while (row < nrows) {
+      const uint32_t m = mask >> row;
+      if (m & 1u) {        // `row` starts interval ib_cur + iv
+        flush(false);
+        cur_cell = __shfl_sync(0xffffffffu, cellv, iv);
+        if (zfill) {
+          const int prevc = iv > 0 ? __shfl_sync(0xffffffffu, cellv, iv - 1) : prev_cell_base;
+          if (cur_cell > prevc + 1) zero_cells(prevc + 1, cur_cell);
+          if (ib_cur + iv == n_intervals - 1 && cur_cell + 1 < total_cells) zero_cells(cur_cell + 1, total_cells);
+        }
+        ++iv;
+        open = true;
+      }
+      const uint32_t rest = m >> 1;
+      const int run = min(nrows - row, rest ? __ffs(rest) : 32);
+      int rr = row;
+      for (; rr + 4 <= row + run; rr += 4) {
+#pragma unroll
+        for (int u = 0; u < QPL; ++u) {
+          const int q = lane + 32 * u;
+          if (q < Q) {
+            const float4 a = rows[(rr + 0) * Q + q], b = rows[(rr + 1) * Q + q];
+            const float4 c = rows[(rr + 2) * Q + q], d = rows[(rr + 3) * Q + q];
+            acc[u].x += a.x; acc[u].y += a.y; acc[u].z += a.z; acc[u].w += a.w;
+            acc[u].x += b.x; acc[u].y += b.y; acc[u].z += b.z; acc[u].w += b.w;
+            acc[u].x += c.x; acc[u].y += c.y; acc[u].z += c.z; acc[u].w += c.w;
+            acc[u].x += d.x; acc[u].y += d.y; acc[u].z += d.z; acc[u].w += d.w;
+          }
+        }
+      }
+      for (; rr < row + run; ++rr) {
+#pragma unroll
+        for (int u = 0; u < QPL; ++u) {
+          const int q = lane + 32 * u;
+          if (q < Q) {
+            const float4 a = rows[rr * Q + q];
+            acc[u].x += a.x; acc[u].y += a.y; acc[u].z += a.z; acc[u].w += a.w;
+          }
+        }
+      }
+      row += run;
+    }
+    __syncwarp();                                  // all lanes are done reading this slot
+    if (it + kPoolStages < n_stages) issue(it + kPoolStages);
+    commit();
+  }
+  // does the open interval continue into the next warp range?
+  const bool continues = R1 < n && !(ibase < n_intervals && __ldg(starts + ibase) == R1);
+  flush(continues);
+}
+
+// one thread per warp range: if the interval holding the range's last row started inside the
+// range and runs past its end, add its pieces (tail of this range + heads of the following ones)
+template <int Q>
+__global__ void bevpool_fwd_tma_fixup_kernel(const int32_t *__restrict__ starts,
+                                             const int32_t *__restrict__ cells, int n,
+                                             int n_intervals, int rows_per_warp, int n_ranges,
+                                             float4 *__restrict__ out,
+                                             const float4 *__restrict__ partial) {
+  const int lane = lane_id();
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int j = wid; j < n_ranges; j += nw) {
+    const long long R0 = (long long)j * rows_per_warp, R1 = min((long long)n, R0 + rows_per_warp);
+    if (R0 >= n || R1 >= n) continue;              // the last range has nothing after it
+    const int iv = find_interval(starts, n_intervals, (int)R1 - 1);
+    if (iv < 0) continue;
+    const int s = __ldg(starts + iv);
+    const int e = iv + 1 < n_intervals ? __ldg(starts + iv + 1) : n;   // intervals tile [0, n)
+    if (s < R0 || e <= R1) continue;               // not the owner, or it ends inside the range
+    const int cell = __ldg(cells + iv);
+    if (cell < 0) continue;
+    const int jl = (int)((e - 1) / rows_per_warp);
+    for (int q = lane; q < Q; q += 32) {
+      float4 r = partial[(2ll * j + 1) * Q + q];
+      for (int jj = j + 1; jj <= jl; ++jj) {
+        const float4 v = partial[(2ll * jj) * Q + q];
+        r.x += v.x; r.y += v.y; r.z += v.z; r.w += v.w;
+      }
+      out[(long long)cell * Q + q] = r;
+    }
+  }
+}
+
 // any channel count: one thread per (interval, channel), like the reference kernel but on the
 // caller's stream and with bounds checks.  Used only when C is not one of the tuned widths.
 __global__ void bevpool_fwd_generic_kernel(const float *__restrict__ x,
@@ -330,9 +593,12 @@ __global__ void bevpool_bwd_generic_kernel(const float *__restrict__ out_grad,
 // ---------------------------------------------------------------------------------------
 // host dispatch
 // ---------------------------------------------------------------------------------------
+constexpr int kTmaMaxRanges = kNumSMs * 8;   // warp ranges of the TMA-staged kernel (<= 8 warps per SM)
 static size_t pool_partial_bytes(int n, int c) {
   size_t nchunks = ((size_t)n + kChunkRows - 1) / kChunkRows;
-  return align_up(2 * nchunks * (size_t)c * sizeof(float));
+  if (nchunks < (size_t)kTmaMaxRanges) nchunks = kTmaMaxRanges;
+  // partial rows (2 per chunk / warp range) + one int32 cell id per interval (<= n of them)
+  return align_up(2 * nchunks * (size_t)c * sizeof(float)) + align_up((size_t)n * sizeof(int32_t));
 }
 
 template <int Q, int G>
@@ -346,6 +612,44 @@ static int launch_fwd(const float *x, const int32_t *perm, const int32_t *geom,
   int fgrid = min((n_intervals + 7) / 8, kNumSMs * 4);
   BEVB200_LAUNCH((bevpool_fwd_fixup_kernel<Q>), fgrid, 256, 0, st, geom, starts, lengths, n,
                  n_intervals, dm, (float4 *)out, (const float4 *)partial);
+  return BEVB200_OK;
+}
+
+template <int Q>
+static int launch_fwd_tma(const float *x, const int32_t *perm, const int32_t *geom,
+                          const int32_t *starts, int n, int c, int n_intervals, PoolDims dm, float *out,
+                          void *ws, int zfill, cudaStream_t st) {
+  size_t nchunks = ((size_t)n + kChunkRows - 1) / kChunkRows;
+  if (nchunks < (size_t)kTmaMaxRanges) nchunks = kTmaMaxRanges;
+  float *partial = (float *)ws;
+  int32_t *cells = (int32_t *)((char *)ws + align_up(2 * nchunks * (size_t)c * sizeof(float)));
+  BEVB200_LAUNCH(pool_interval_cells_kernel, grid_for(n_intervals, 256), 256, 0, st, geom, starts, n,
+                 n_intervals, dm, cells);
+  const size_t stage_bytes = (size_t)kStageRows * Q * 16;
+  int warps = (int)((200 * 1024) / (kPoolStages * stage_bytes));
+  if (warps > 8) warps = 8;
+  if (warps < 1) warps = 1;
+  const size_t smem = (size_t)warps * kPoolStages * stage_bytes;
+  const int n_ranges_max = kNumSMs * warps;
+  int rpw = (int)(((long long)n + n_ranges_max - 1) / n_ranges_max);
+  rpw = (rpw + kStageRows - 1) / kStageRows * kStageRows;
+  const int n_ranges = (n + rpw - 1) / rpw;
+  const int grid = (n_ranges + warps - 1) / warps;
+  if (perm) {
+    BEVB200_CUDA(cudaFuncSetAttribute(bevpool_fwd_tma_kernel<Q, true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BEVB200_LAUNCH((bevpool_fwd_tma_kernel<Q, true>), grid, warps * 32, smem, st, (const float4 *)x, perm,
+                   starts, cells, n, n_intervals, rpw, zfill, dm.b * dm.d * dm.h * dm.w, (float4 *)out,
+                   (float4 *)partial);
+  } else {
+    BEVB200_CUDA(cudaFuncSetAttribute(bevpool_fwd_tma_kernel<Q, false>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BEVB200_LAUNCH((bevpool_fwd_tma_kernel<Q, false>), grid, warps * 32, smem, st, (const float4 *)x, perm,
+                   starts, cells, n, n_intervals, rpw, zfill, dm.b * dm.d * dm.h * dm.w, (float4 *)out,
+                   (float4 *)partial);
+  }
+  BEVB200_LAUNCH((bevpool_fwd_tma_fixup_kernel<Q>), (n_ranges * 32 + 255) / 256, 256, 0, st, starts, cells, n,
+                 n_intervals, rpw, n_ranges, (float4 *)out, (const float4 *)partial);
   return BEVB200_OK;
 }
 
@@ -373,17 +677,33 @@ static int launch_bwd(const float *og, const int32_t *perm, const int32_t *geom,
     default: FALLBACK; break;                    \
   }
 
+// 0 = TMA-staged streaming kernel (default), 1 = register-gather kernel (v1).  Selected by the
+// environment variable BEVB200_POOL_VARIANT at first use (kept for A/B measurements).
+static int g_pool_variant = -1;
+
 static int pool_forward(int b, int d, int h, int w, int n, int c, int n_intervals, const float *x,
                         const int32_t *perm, const int32_t *geom, const int32_t *starts,
                         const int32_t *lengths, float *out, void *ws, size_t ws_bytes,
-                        void *stream) {
+                        void *stream, bool trust_tables) {
   BEVB200_REQUIRE(b > 0 && d > 0 && h > 0 && w > 0 && c > 0, "bad output shape");
   BEVB200_REQUIRE(n >= 0 && n_intervals >= 0, "negative size");
   BEVB200_REQUIRE(out != nullptr, "null out");
   BEVB200_REQUIRE((long long)b * d * h * w * c < (1ll << 40), "output too large");
+  BEVB200_REQUIRE((long long)b * d * h * w < (1ll << 31), "grid has too many cells");
+  if (g_pool_variant < 0) {
+    const char *e = getenv("BEVB200_POOL_VARIANT");
+    g_pool_variant = (e && e[0] == '1') ? 1 : 0;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   size_t out_bytes = (size_t)b * d * h * w * c * sizeof(float);
-  BEVB200_CUDA(cudaMemsetAsync(out, 0, out_bytes, st));
+  // plan tables (perm != null) with B*D == 1 are in ascending cell order: the pooling kernel
+  // zero-fills the empty cells itself; every other case pre-zeroes the grid
+  bool tuned = false;
+  switch (c) { case 16: case 32: case 64: case 80: case 96: case 128: case 160: case 256: tuned = true; }
+  const bool aligned16 = ((uintptr_t)x % 16 == 0) && ((uintptr_t)out % 16 == 0);
+  const int zfill = (perm != nullptr && b * d == 1 && n > 0 && n_intervals > 0 && tuned && aligned16 &&
+                     g_pool_variant == 0 && trust_tables) ? 1 : 0;
+  if (!zfill) BEVB200_CUDA(cudaMemsetAsync(out, 0, out_bytes, st));
   if (n == 0 || n_intervals == 0) return BEVB200_OK;
   BEVB200_REQUIRE(x && geom && starts && lengths, "null input");
   PoolDims dm{b, d, h, w};
@@ -396,7 +716,10 @@ static int pool_forward(int b, int d, int h, int w, int n, int c, int n_interval
                ws_bytes, pool_partial_bytes(n, c));                                            \
       return BEVB200_EWORKSPACE;                                                               \
     }                                                                                          \
-    rc = launch_fwd<Q, G>(x, perm, geom, starts, lengths, n, n_intervals, dm, out, (float *)ws, st); \
+    if (g_pool_variant == 1)                                                                   \
+      rc = launch_fwd<Q, G>(x, perm, geom, starts, lengths, n, n_intervals, dm, out, (float *)ws, st); \
+    else                                                                                       \
+      rc = launch_fwd_tma<Q>(x, perm, geom, starts, n, c, n_intervals, dm, out, ws, zfill, st);  \
   } while (0)
 #define CALL_FWD_GENERIC()                                                                     \
   do {                                                                                         \
@@ -600,7 +923,7 @@ int bevb200_bev_pool(int b, int d, int h, int w, int n, int c, int n_intervals, 
                      const int32_t *interval_lengths, float *out, void *workspace,
                      size_t workspace_bytes, void *stream) {
   return pool_forward(b, d, h, w, n, c, n_intervals, x, nullptr, geom_feats, interval_starts,
-                      interval_lengths, out, workspace, workspace_bytes, stream);
+                      interval_lengths, out, workspace, workspace_bytes, stream, false);
 }
 
 int bevb200_bev_pool_perm(int b, int d, int h, int w, int n, int c, int n_intervals,
@@ -609,7 +932,7 @@ int bevb200_bev_pool_perm(int b, int d, int h, int w, int n, int c, int n_interv
                           float *out, void *workspace, size_t workspace_bytes, void *stream) {
   BEVB200_REQUIRE(perm != nullptr || n == 0, "null perm");
   return pool_forward(b, d, h, w, n, c, n_intervals, x, perm, geom_feats, interval_starts,
-                      interval_lengths, out, workspace, workspace_bytes, stream);
+                      interval_lengths, out, workspace, workspace_bytes, stream, true);
 }
 
 int bevb200_bev_pool_grad(int b, int d, int h, int w, int n, int c, int n_intervals,

@@ -24,6 +24,8 @@
 //
 // BEVB200_PREC_TF32X3 keeps fp32-class accuracy (error ~2^-21 per product) at 3 MMAs per K
 // step; BEVB200_PREC_TF32 issues only hi*hi (single-pass TF32, ~1e-3 relative).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace bevb200 {
@@ -116,7 +118,8 @@ __host__ __device__ inline uint32_t umma_idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-struct TcParams {
+// ---- v2: one tile per CTA, combined A+B stages, two CTAs per SM when the stages are small ----
+struct TcParamsV2 {
   const float *features;
   const float *wpacked;   // [K][nkb][nsplit][Cout][32] floats, swizzled smem image
   const int32_t *nbr;
@@ -130,7 +133,7 @@ struct TcParams {
 };
 
 template <int NSPLIT>
-__global__ void __launch_bounds__(kTcThreads, 2) spconv_tc_kernel(const TcParams p) {
+__global__ void __launch_bounds__(kTcThreads, 2) spconv_tc_kernel_v2(const TcParamsV2 p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // align the stage area to 1024 B (SWIZZLE_128B atoms)
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -321,6 +324,527 @@ __global__ void __launch_bounds__(kTcThreads, 2) spconv_tc_kernel(const TcParams
   }
 }
 
+// ---- v3: persistent, warp-specialised, separate weight ring, double-buffered accumulator ----
+struct TcParams {
+  const float *features;
+  const float *wpacked;   // [nkb][nsplit][Cout][32] floats, swizzled smem image
+  const int32_t *nbr;
+  const float *scale, *shift, *residual;
+  float *out;
+  int n_in, n_out, c_in, c_out, kvol, relu;
+  int nkb;        // K blocks of 32 floats over the concatenated (offset, channel) axis
+  int cin_shift;  // log2(c_in): c_in is a power of two >= 16 on this path
+  int nsa, nsb;   // depth of the A (gathered features) and B (weights) rings
+  int acc_cols;   // TMEM columns of one accumulator (>= 32); two are allocated
+  int num_tiles;
+};
+
+// Warp roles of the persistent kernel (448 threads, one CTA per SM):
+//   0-7   A producers   gather feature rows -> tf32 hi/lo split -> swizzled smem (A ring)
+//   8     MMA issuer    lane 0 issues tcgen05.mma, commits ring slots / accumulators
+//   9     B loader      lane 0 streams the packed weights with cp.async.bulk (B ring)
+//   10-13 epilogue      tcgen05.ld the finished accumulator, BN/residual/ReLU, store
+// The accumulator is double buffered in TMEM, so the epilogue of tile i overlaps the main loop
+// of tile i+1; the A and B rings run continuously across tile boundaries.
+constexpr int kTcWarpsProducer = 8;
+constexpr int kTcWarpMma = 8, kTcWarpB = 9, kTcWarpEpi0 = 10;
+constexpr int kTcThreadsV3 = 14 * 32;
+constexpr int kMaxStages = 8;
+
+template <int NSPLIT>
+__global__ void __launch_bounds__(kTcThreadsV3, 1) spconv_tc_kernel(const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B atoms
+  uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int a_stage_bytes = NSPLIT * kABlockBytes;
+  const int b_part_bytes = p.c_out * 128;                               // Cout rows x 128 B
+  const int b_stage_bytes = NSPLIT * b_part_bytes;
+  const uint32_t a_ring = smem_base;
+  const uint32_t b_ring = a_ring + (uint32_t)(p.nsa * a_stage_bytes);
+  int32_t *nbr_s = reinterpret_cast<int32_t *>(smem + (size_t)p.nsa * a_stage_bytes +
+                                               (size_t)p.nsb * b_stage_bytes);   // [2][kvol][128]
+  __shared__ uint64_t bars[4 * kMaxStages + 4];
+  __shared__ uint32_t tmem_base_s;
+  const uint32_t a_full = smem_u32(&bars[0]), a_empty = smem_u32(&bars[kMaxStages]);
+  const uint32_t b_full = smem_u32(&bars[2 * kMaxStages]), b_empty = smem_u32(&bars[3 * kMaxStages]);
+  const uint32_t acc_full = smem_u32(&bars[4 * kMaxStages]), acc_empty = smem_u32(&bars[4 * kMaxStages + 2]);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nkb = p.nkb;
+
+  if (tid == 0) {
+    for (int s = 0; s < p.nsa; ++s) {
+      mbar_init(a_full + 8 * s, kTcProducerThreads);
+      mbar_init(a_empty + 8 * s, 1);
+    }
+    for (int s = 0; s < p.nsb; ++s) {
+      mbar_init(b_full + 8 * s, 1);
+      mbar_init(b_empty + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(acc_full + 8 * b, 1);
+      mbar_init(acc_empty + 8 * b, 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kTcWarpMma) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)(2 * p.acc_cols)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp < kTcWarpsProducer) {
+    // =============================== A producers =========================================
+    const int r = tid & 127, half = tid >> 7;
+    const uint32_t sw = (uint32_t)(r & 7);
+    const uint32_t row_off = (uint32_t)r * 128u;
+    const int nbr_elems = p.kvol * kTileM;            // per tile
+    constexpr int kNbrPerThread = (27 * kTileM + kTcProducerThreads - 1) / kTcProducerThreads;  // 14
+
+    auto load_nbr = [&](int tile, int i) -> int {     // element i of the tile's [kvol][128] table
+      const int k = i >> 7, rr = i & 127, o = tile * kTileM + rr;
+      int v = (tile < p.num_tiles && o < p.n_out) ? __ldg(p.nbr + (long long)k * p.n_out + o) : -1;
+      return v >= p.n_in ? -1 : v;
+    };
+    // first tile's table straight to smem buffer 0
+    for (int i = tid; i < nbr_elems; i += kTcProducerThreads) nbr_s[i] = load_nbr(blockIdx.x, i);
+    asm volatile("bar.sync 1, %0;" ::"n"(kTcProducerThreads) : "memory");
+
+    // concatenated-K block `it` of tile-local index covers K indices [32*it, 32*it+32); this
+    // thread owns 16 of them (4 float4), inside ONE kernel offset because c_in % 16 == 0
+    auto issue = [&](const int32_t *tbl, int it, float4 (&v)[4]) {
+      const int kk = it * kKBlock + half * 16;
+      const int k = kk >> p.cin_shift;
+      const int ch = kk & (p.c_in - 1);
+      const int src = k < p.kvol ? tbl[k * kTileM + r] : -1;
+      if (src >= 0) {
+        const float4 *q = reinterpret_cast<const float4 *>(p.features + (long long)src * p.c_in + ch);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = __ldg(q + j);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    constexpr int PD = 4;  // register prefetch distance (K blocks in flight per thread)
+    float4 v[PD][4];
+    // the CTA's K-block stream: g = local_tile * nkb + it
+    const int my_tiles = blockIdx.x < p.num_tiles ? (p.num_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    const long long g_total = (long long)my_tiles * nkb;
+    auto issue_g = [&](long long g, float4 (&vv)[4]) {
+      const int lt = (int)(g / nkb), it = (int)(g - (long long)lt * nkb);
+      issue(nbr_s + (lt & 1) * nbr_elems, it, vv);
+    };
+#pragma unroll
+    for (int j = 0; j < PD; ++j)
+      if (j < g_total && j < nkb) issue_g(j, v[j]);   // only the first tile's table is staged yet
+    int nxt[kNbrPerThread];
+    for (long long g0 = 0; g0 < g_total; g0 += PD) {
+#pragma unroll
+      for (int jj = 0; jj < PD; ++jj) {
+        const long long g = g0 + jj;
+        if (g < g_total) {
+          const int lt = (int)(g / nkb), it = (int)(g - (long long)lt * nkb);
+          const int next_tile = blockIdx.x + (lt + 1) * gridDim.x;
+          if (it == 0) {
+            // fetch the NEXT tile's neighbour table into registers (lands in smem mid-tile)
+#pragma unroll
+            for (int u = 0; u < kNbrPerThread; ++u) {
+              const int i = tid + u * kTcProducerThreads;
+              nxt[u] = i < nbr_elems ? load_nbr(next_tile, i) : -1;
+            }
+          }
+          if (it == nkb / 2) {
+            int32_t *dstt = nbr_s + ((lt + 1) & 1) * nbr_elems;
+#pragma unroll
+            for (int u = 0; u < kNbrPerThread; ++u) {
+              const int i = tid + u * kTcProducerThreads;
+              if (i < nbr_elems) dstt[i] = nxt[u];
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kTcProducerThreads) : "memory");
+          }
+          const int s = (int)(g % p.nsa);
+          const uint32_t ph = (uint32_t)(g / p.nsa) & 1u;
+          mbar_wait(a_empty + 8 * s, ph ^ 1u);
+          const uint32_t stage = a_ring + (uint32_t)s * (uint32_t)a_stage_bytes;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t chunk = (uint32_t)(half * 4 + j);
+            const uint32_t off = row_off + ((chunk ^ sw) << 4);
+            uint4 hi;
+            hi.x = __float_as_uint(v[jj][j].x) & 0xffffe000u;
+            hi.y = __float_as_uint(v[jj][j].y) & 0xffffe000u;
+            hi.z = __float_as_uint(v[jj][j].z) & 0xffffe000u;
+            hi.w = __float_as_uint(v[jj][j].w) & 0xffffe000u;
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(stage + off), "r"(hi.x), "r"(hi.y),
+                         "r"(hi.z), "r"(hi.w) : "memory");
+            if (NSPLIT == 2) {
+              float4 lo;
+              lo.x = v[jj][j].x - __uint_as_float(hi.x);
+              lo.y = v[jj][j].y - __uint_as_float(hi.y);
+              lo.z = v[jj][j].z - __uint_as_float(hi.z);
+              lo.w = v[jj][j].w - __uint_as_float(hi.w);
+              asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stage + kABlockBytes + off),
+                           "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
+            }
+          }
+          fence_proxy_async();     // generic-proxy stores -> visible to the tensor core (async proxy)
+          mbar_arrive(a_full + 8 * s);
+          // prefetch PD blocks ahead; the next tile's table is in smem once it >= nkb/2 of this
+          // tile, and PD <= nkb - nkb/2 always holds (nkb >= 12 on this path)
+          if (g + PD < g_total) issue_g(g + PD, v[jj]);
+        }
+      }
+    }
+  } else if (warp == kTcWarpMma) {
+    // =============================== MMA issuer ==========================================
+    const uint32_t idesc = umma_idesc_tf32(kTileM, p.c_out);
+    long long g = 0;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
+      const int ab = lt & 1;
+      mbar_wait(acc_empty + 8 * ab, ((uint32_t)(lt >> 1) & 1u) ^ 1u);   // epilogue drained this buffer
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(ab * p.acc_cols);
+      for (int it = 0; it < nkb; ++it, ++g) {
+        const int sa = (int)(g % p.nsa), sb = (int)(g % p.nsb);
+        mbar_wait(a_full + 8 * sa, (uint32_t)(g / p.nsa) & 1u);
+        mbar_wait(b_full + 8 * sb, (uint32_t)(g / p.nsb) & 1u);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t astage = a_ring + (uint32_t)sa * (uint32_t)a_stage_bytes;
+          const uint32_t bstage = b_ring + (uint32_t)sb * (uint32_t)b_stage_bytes;
+          const uint64_t a_hi = umma_desc_sw128(astage);
+          const uint64_t a_lo = umma_desc_sw128(astage + kABlockBytes);
+          const uint64_t b_hi = umma_desc_sw128(bstage);
+          const uint64_t b_lo = umma_desc_sw128(bstage + b_part_bytes);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t adv = (uint64_t)(ks * 2);  // +32 B along K inside the 128-byte swizzle row
+            if (NSPLIT == 2) {
+              tc_mma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+              tc_mma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+              tc_mma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
+            } else {
+              tc_mma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+            }
+          }
+          tc_commit(a_empty + 8 * sa);
+          tc_commit(b_empty + 8 * sb);
+          if (it == nkb - 1) tc_commit(acc_full + 8 * ab);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == kTcWarpB) {
+    // =============================== B loader ============================================
+    if (lane == 0) {
+      long long g = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        for (int it = 0; it < nkb; ++it, ++g) {
+          const int sb = (int)(g % p.nsb);
+          mbar_wait(b_empty + 8 * sb, ((uint32_t)(g / p.nsb) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(b_full + 8 * sb, (uint32_t)b_stage_bytes);
+          bulk_copy_g2s(b_ring + (uint32_t)sb * (uint32_t)b_stage_bytes,
+                        p.wpacked + (long long)it * (long long)(NSPLIT * p.c_out * 32),
+                        (uint32_t)b_stage_bytes, b_full + 8 * sb);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // =============================== epilogue warps ======================================
+    const int q = warp & 3;                           // TMEM lane quarter this warp may access
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
+      const int ab = lt & 1;
+      mbar_wait(acc_full + 8 * ab, (uint32_t)(lt >> 1) & 1u);
+      tc_fence_after();
+      const int orow = tile * kTileM + q * 32 + lane;  // accumulator lane == output row of the tile
+      const uint32_t t_addr = tmem_base + (uint32_t)(ab * p.acc_cols) + ((uint32_t)(q * 32) << 16);
+      for (int c0 = 0; c0 < p.c_out; c0 += 16) {
+        float acc[16];
+        tc_ld16(t_addr + (uint32_t)c0, acc);
+        if (orow < p.n_out) {
+          float *dst = p.out + (long long)orow * p.c_out + c0;
+          const float *res = p.residual ? p.residual + (long long)orow * p.c_out + c0 : nullptr;
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            float y[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float t = acc[j + e];
+              if (p.scale) t *= __ldg(p.scale + c0 + j + e);
+              if (p.shift) t += __ldg(p.shift + c0 + j + e);
+              y[e] = t;
+            }
+            if (res) {
+              const float4 rv = __ldg(reinterpret_cast<const float4 *>(res + j));
+              y[0] += rv.x; y[1] += rv.y; y[2] += rv.z; y[3] += rv.w;
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) y[e] = fmaxf(y[e], 0.f);
+            }
+            *reinterpret_cast<float4 *>(dst + j) = make_float4(y[0], y[1], y[2], y[3]);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(acc_empty + 8 * ab);                 // this thread is done with the TMEM buffer
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kTcWarpMma) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)(2 * p.acc_cols)) : "memory");
+  }
+}
+
+// ---- v4: A operand in TENSOR MEMORY (tcgen05.mma TS form) ------------------------------------
+// Measured on v2: with both operands in shared memory the M128 x N x K8 tf32 MMA re-reads the
+// 4 KB A tile from smem on every instruction (3 per K step with the 3xTF32 split), which on top
+// of the producers' stores saturates the 128 B/clk shared-memory port -- the kernel was smem
+// bound, not tensor bound.  Here the producers write the split A rows straight from registers
+// into TMEM (tcgen05.st 32x32b.x16: thread = row = TMEM lane, 16 K values = 16 columns), the MMA
+// takes A from TMEM, and shared memory only carries the weights (B): a deep cp.async.bulk ring
+// fed by its own warp.  Layout of the 256 TMEM columns of a CTA (two CTAs per SM):
+//   [0, acc_cols)            fp32 accumulator, 128 lanes x Cout
+//   [acc_cols + 64*s ...)    A ring stage s: 32 columns hi | 32 columns lo   (K block of 32)
+constexpr int kV4Threads = 10 * 32;   // warps 0-7 producers/epilogue, 8 MMA issuer, 9 weight loader
+
+struct TcParamsV4 {
+  const float *features;
+  const float *wpacked;
+  const int32_t *nbr;
+  const float *scale, *shift, *residual;
+  float *out;
+  int n_in, n_out, c_in, c_out, kvol, relu;
+  int nkb, cin_shift;
+  int nsa, nsb;       // TMEM A-ring stages, smem B-ring stages
+  int acc_cols;       // accumulator columns (>= 32)
+  int tmem_cols;      // allocation (power of two >= acc_cols + nsa * nsplit * 32)
+};
+
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+template <int NSPLIT>
+__global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v4(const TcParamsV4 p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int b_part_bytes = p.c_out * 128;
+  const int b_stage_bytes = NSPLIT * b_part_bytes;
+  __shared__ uint64_t bars[4 * kMaxStages + 1];
+  __shared__ uint32_t tmem_base_s;
+  const uint32_t a_full = smem_u32(&bars[0]), a_empty = smem_u32(&bars[kMaxStages]);
+  const uint32_t b_full = smem_u32(&bars[2 * kMaxStages]), b_empty = smem_u32(&bars[3 * kMaxStages]);
+  const uint32_t accbar = smem_u32(&bars[4 * kMaxStages]);
+  int32_t *nbr_s = reinterpret_cast<int32_t *>(smem + (size_t)p.nsb * b_stage_bytes);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row0 = blockIdx.x * kTileM;
+  const int n_iters = p.nkb;
+
+  if (tid == 0) {
+    for (int s = 0; s < p.nsa; ++s) {
+      mbar_init(a_full + 8 * s, kTcProducerThreads);
+      mbar_init(a_empty + 8 * s, 1);
+    }
+    for (int s = 0; s < p.nsb; ++s) {
+      mbar_init(b_full + 8 * s, 1);
+      mbar_init(b_empty + 8 * s, 1);
+    }
+    mbar_init(accbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t a_ring = tmem_base + (uint32_t)p.acc_cols;       // column offset of A stage 0
+  constexpr uint32_t kAStageCols = NSPLIT * 32;
+
+  if (warp < 8) {
+    // =============================== producers ===========================================
+    // TMEM lane quarter q = warp & 3 is the only one this warp may touch: row = 32 q + lane
+    const int q = warp & 3, half = warp >> 2;
+    const int r = q * 32 + lane;
+    for (int i = tid; i < p.kvol * kTileM; i += kTcProducerThreads) {
+      const int k = i >> 7, rr = i & 127, o = row0 + rr;
+      int v = o < p.n_out ? __ldg(p.nbr + (long long)k * p.n_out + o) : -1;
+      if (v >= p.n_in) v = -1;
+      nbr_s[i] = v;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kTcProducerThreads) : "memory");
+
+    auto issue = [&](int it, float4 (&v)[4]) {
+      const int kk = it * kKBlock + half * 16;
+      const int k = kk >> p.cin_shift;
+      const int ch = kk & (p.c_in - 1);
+      const int src = k < p.kvol ? nbr_s[k * kTileM + r] : -1;
+      if (src >= 0) {
+        const float4 *g = reinterpret_cast<const float4 *>(p.features + (long long)src * p.c_in + ch);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = __ldg(g + j);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    constexpr int PD = 4;
+    float4 v[PD][4];
+#pragma unroll
+    for (int j = 0; j < PD; ++j)
+      if (j < n_iters) issue(j, v[j]);
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    for (int it0 = 0; it0 < n_iters; it0 += PD) {
+#pragma unroll
+      for (int jj = 0; jj < PD; ++jj) {
+        const int it = it0 + jj;
+        if (it < n_iters) {
+          const int s = it % p.nsa;
+          const uint32_t ph = (uint32_t)(it / p.nsa) & 1u;
+          mbar_wait(a_empty + 8 * s, ph ^ 1u);
+          tc_fence_after();
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float f[4] = {v[jj][j].x, v[jj][j].y, v[jj][j].z, v[jj][j].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              hi[4 * j + e] = __float_as_uint(f[e]) & 0xffffe000u;
+              lo[4 * j + e] = __float_as_uint(f[e] - __uint_as_float(hi[4 * j + e]));
+            }
+          }
+          const uint32_t col = a_ring + (uint32_t)s * kAStageCols + (uint32_t)(half * 16);
+          tc_st16(lane_base + col, hi);
+          if (NSPLIT == 2) tc_st16(lane_base + col + 32u, lo);
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          tc_fence_before();
+          mbar_arrive(a_full + 8 * s);
+          if (it + PD < n_iters) issue(it + PD, v[jj]);
+        }
+      }
+    }
+    // =============================== epilogue ============================================
+    mbar_wait(accbar, 0);
+    tc_fence_after();
+    const int orow = row0 + q * 32 + lane;
+    const int ncol_half = p.c_out / 2;
+    const int col_begin = half * ncol_half;
+    for (int c0 = col_begin; c0 < col_begin + ncol_half; c0 += 16) {
+      float acc[16];
+      tc_ld16(tmem_base + lane_base + (uint32_t)c0, acc);
+      if (orow < p.n_out) {
+        float *dst = p.out + (long long)orow * p.c_out + c0;
+        const float *res = p.residual ? p.residual + (long long)orow * p.c_out + c0 : nullptr;
+        const int ncols = min(16, col_begin + ncol_half - c0);
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          if (j < ncols) {
+            float y[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float t = acc[j + e];
+              if (p.scale) t *= __ldg(p.scale + c0 + j + e);
+              if (p.shift) t += __ldg(p.shift + c0 + j + e);
+              y[e] = t;
+            }
+            if (res) {
+              const float4 rv = __ldg(reinterpret_cast<const float4 *>(res + j));
+              y[0] += rv.x; y[1] += rv.y; y[2] += rv.z; y[3] += rv.w;
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) y[e] = fmaxf(y[e], 0.f);
+            }
+            *reinterpret_cast<float4 *>(dst + j) = make_float4(y[0], y[1], y[2], y[3]);
+          }
+        }
+      }
+    }
+  } else if (warp == 8) {
+    // =============================== MMA issuer ==========================================
+    const uint32_t idesc = umma_idesc_tf32(kTileM, p.c_out);
+    for (int it = 0; it < n_iters; ++it) {
+      const int sa = it % p.nsa, sb = it % p.nsb;
+      mbar_wait(a_full + 8 * sa, (uint32_t)(it / p.nsa) & 1u);
+      mbar_wait(b_full + 8 * sb, (uint32_t)(it / p.nsb) & 1u);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_hi = a_ring + (uint32_t)sa * kAStageCols;   // lane 0, column offset
+        const uint32_t a_lo = a_hi + 32u;
+        const uint32_t bstage = smem_base + (uint32_t)sb * (uint32_t)b_stage_bytes;
+        const uint64_t b_hi = umma_desc_sw128(bstage);
+        const uint64_t b_lo = umma_desc_sw128(bstage + b_part_bytes);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t badv = (uint64_t)(ks * 2);   // +32 B along K inside the swizzled row
+          const uint32_t aadv = (uint32_t)(ks * 8);   // +8 tf32 = 8 TMEM columns
+          if (NSPLIT == 2) {
+            tc_mma_tf32_ts(tmem_base, a_lo + aadv, b_hi + badv, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+            tc_mma_tf32_ts(tmem_base, a_hi + aadv, b_lo + badv, idesc, 1u);
+            tc_mma_tf32_ts(tmem_base, a_hi + aadv, b_hi + badv, idesc, 1u);
+          } else {
+            tc_mma_tf32_ts(tmem_base, a_hi + aadv, b_hi + badv, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+          }
+        }
+        tc_commit(a_empty + 8 * sa);
+        tc_commit(b_empty + 8 * sb);
+        if (it == n_iters - 1) tc_commit(accbar);
+      }
+      __syncwarp();
+    }
+  } else {
+    // =============================== weight loader =======================================
+    if (lane == 0) {
+      for (int it = 0; it < n_iters; ++it) {
+        const int sb = it % p.nsb;
+        mbar_wait(b_empty + 8 * sb, ((uint32_t)(it / p.nsb) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(b_full + 8 * sb, (uint32_t)b_stage_bytes);
+        bulk_copy_g2s(smem_base + (uint32_t)sb * (uint32_t)b_stage_bytes,
+                      p.wpacked + (long long)it * (long long)(NSPLIT * p.c_out * 32),
+                      (uint32_t)b_stage_bytes, b_full + 8 * sb);
+      }
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
 // weight [K][Cin][Cout] fp32 -> packed [nkb][nsplit][Cout][32] in the swizzled smem image.  The K
 // axis is the concatenation over kernel offsets of the Cin channels (kk = k*Cin + ci), cut into
 // blocks of 32; element (n, c) of block kb sits at float index n*32 + (((c/4) ^ (n&7)) * 4) + (c%4).
@@ -394,18 +918,43 @@ int spconv_forward_tc(const float *features, const float *weight, const float *p
   p.nkb = tc_nkb(c_in, kvol);
   p.cin_shift = 0;
   while ((1 << p.cin_shift) < c_in) ++p.cin_shift;
-  p.tmem_cols = c_out < 32 ? 32 : c_out;
-  const int stage_bytes = nsplit * (kABlockBytes + c_out * 128);
-  // two CTAs per SM when the stages are small enough (overlaps one tile's epilogue with the
-  // other's main loop); otherwise one CTA with a deeper ring
-  const int nbr_bytes = kvol * kTileM * 4;
-  int ns = 2;
-  if (2 * stage_bytes + nbr_bytes + 1024 > 111 * 1024) {
-    ns = (215 * 1024 - nbr_bytes) / stage_bytes;
-    if (ns > 4) ns = 4;
+  p.acc_cols = c_out < 32 ? 32 : c_out;
+  p.num_tiles = (n_out + kTileM - 1) / kTileM;
+  // shared-memory rings: 3 A stages (gathered rows, 16 KB per split part) + as many weight
+  // stages as fit (deep prefetch hides the L2 latency of the per-K-block weight fetch)
+  const int a_stage = nsplit * kABlockBytes, b_stage = nsplit * c_out * 128;
+  const int nbr_bytes = 2 * kvol * kTileM * 4;
+  p.nsa = 3;
+  int nsb = (225 * 1024 - nbr_bytes - p.nsa * a_stage) / b_stage;
+  if (nsb > kMaxStages) nsb = kMaxStages;
+  if (nsb < 2) nsb = 2;
+  p.nsb = nsb;
+  const size_t smem = (size_t)p.nsa * a_stage + (size_t)p.nsb * b_stage + nbr_bytes + 1024;
+  // kernel variant: v2 (tile per CTA, 2 CTAs/SM) or v3 (persistent).  BEVB200_SPCONV_TC_VARIANT
+  // = 2 / 3 forces one; the default picks per shape from measurements.
+  static int forced = -1;
+  if (forced < 0) {
+    const char *e = getenv("BEVB200_SPCONV_TC_VARIANT");
+    forced = e ? atoi(e) : 0;
   }
-  p.nstages = ns;
-  const size_t smem = (size_t)ns * stage_bytes + nbr_bytes + 1024;
+  int variant = forced ? forced : 4;
+  if (variant == 3 && p.nkb < 12) variant = 2;   // v3's cross-tile prefetch needs >= 12 K blocks per tile
+  TcParamsV2 p2;
+  p2.features = features; p2.nbr = nbr; p2.scale = scale; p2.shift = shift; p2.residual = residual;
+  p2.out = out; p2.n_in = n_in; p2.n_out = n_out; p2.c_in = c_in; p2.c_out = c_out; p2.kvol = kvol;
+  p2.relu = relu; p2.nkb = p.nkb; p2.cin_shift = p.cin_shift; p2.tmem_cols = p.acc_cols;
+  size_t smem2 = 0;
+  {
+    const int stage_bytes = nsplit * (kABlockBytes + c_out * 128);
+    const int nbr1 = kvol * kTileM * 4;
+    int ns = 2;
+    if (2 * stage_bytes + nbr1 + 1024 > 111 * 1024) {
+      ns = (215 * 1024 - nbr1) / stage_bytes;
+      if (ns > 4) ns = 4;
+    }
+    p2.nstages = ns;
+    smem2 = (size_t)ns * stage_bytes + nbr1 + 1024;
+  }
   float *packed = nullptr;
   if (packed_in == nullptr) {
     BEVB200_CUDA(cudaMallocAsync((void **)&packed, spconv_packed_bytes(c_in, c_out, kvol, precision), st));
@@ -415,15 +964,59 @@ int spconv_forward_tc(const float *features, const float *weight, const float *p
   } else {
     p.wpacked = packed_in;
   }
-  const int grid = (n_out + kTileM - 1) / kTileM;
+  p2.wpacked = p.wpacked;
+  if (variant == 4) {
+    TcParamsV4 p4;
+    p4.features = features; p4.nbr = nbr; p4.scale = scale; p4.shift = shift; p4.residual = residual;
+    p4.out = out; p4.n_in = n_in; p4.n_out = n_out; p4.c_in = c_in; p4.c_out = c_out; p4.kvol = kvol;
+    p4.relu = relu; p4.nkb = p.nkb; p4.cin_shift = p.cin_shift; p4.wpacked = p.wpacked;
+    p4.acc_cols = p.acc_cols;
+    // 256 TMEM columns per CTA (two CTAs per SM): accumulator + A ring
+    p4.nsa = (256 - p4.acc_cols) / (nsplit * 32);
+    if (p4.nsa > 4) p4.nsa = 4;
+    p4.tmem_cols = 256;
+    const int b_stage4 = nsplit * c_out * 128, nbr4 = kvol * kTileM * 4;
+    int nsb4 = (110 * 1024 - nbr4 - 1024) / b_stage4;
+    if (nsb4 > kMaxStages) nsb4 = kMaxStages;
+    if (nsb4 < 2) nsb4 = 2;
+    p4.nsb = nsb4;
+    const size_t smem4 = (size_t)nsb4 * b_stage4 + nbr4 + 1024;
+    const int grid4 = (n_out + kTileM - 1) / kTileM;
+    if (nsplit == 2) {
+      BEVB200_CUDA(cudaFuncSetAttribute(spconv_tc_kernel_v4<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem4));
+      BEVB200_LAUNCH(spconv_tc_kernel_v4<2>, grid4, kV4Threads, smem4, st, p4);
+    } else {
+      BEVB200_CUDA(cudaFuncSetAttribute(spconv_tc_kernel_v4<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem4));
+      BEVB200_LAUNCH(spconv_tc_kernel_v4<1>, grid4, kV4Threads, smem4, st, p4);
+    }
+    if (packed) BEVB200_CUDA(cudaFreeAsync(packed, st));
+    return BEVB200_OK;
+  }
+  if (variant == 2) {
+    const int grid2 = (n_out + kTileM - 1) / kTileM;
+    if (nsplit == 2) {
+      BEVB200_CUDA(cudaFuncSetAttribute(spconv_tc_kernel_v2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem2));
+      BEVB200_LAUNCH(spconv_tc_kernel_v2<2>, grid2, kTcThreads, smem2, st, p2);
+    } else {
+      BEVB200_CUDA(cudaFuncSetAttribute(spconv_tc_kernel_v2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem2));
+      BEVB200_LAUNCH(spconv_tc_kernel_v2<1>, grid2, kTcThreads, smem2, st, p2);
+    }
+    if (packed) BEVB200_CUDA(cudaFreeAsync(packed, st));
+    return BEVB200_OK;
+  }
+  const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;   // persistent: one CTA per SM
   if (nsplit == 2) {
     BEVB200_CUDA(cudaFuncSetAttribute(spconv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
-    BEVB200_LAUNCH(spconv_tc_kernel<2>, grid, kTcThreads, smem, st, p);
+    BEVB200_LAUNCH(spconv_tc_kernel<2>, grid, kTcThreadsV3, smem, st, p);
   } else {
     BEVB200_CUDA(cudaFuncSetAttribute(spconv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
-    BEVB200_LAUNCH(spconv_tc_kernel<1>, grid, kTcThreads, smem, st, p);
+    BEVB200_LAUNCH(spconv_tc_kernel<1>, grid, kTcThreadsV3, smem, st, p);
   }
   if (packed) BEVB200_CUDA(cudaFreeAsync(packed, st));
   return BEVB200_OK;

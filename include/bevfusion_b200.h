@@ -84,8 +84,11 @@ BEVB200_API int bevb200_bev_pool_grad(int b, int d, int h, int w, int n, int c, 
  * the sorted->original row map produced by bevb200_bev_pool_prepare_*, so that the
  * caller never materialises x[kept][argsort] (base.py:168, bev_pool.py:94).
  *   x / x_grad  [n_total, c] in ORIGINAL (unsorted, unfiltered) order
- *   perm        [n] int32, perm[i] = original row of sorted row i
- * bev_pool_grad_perm zero-fills the rows of x_grad that were filtered out. */
+ *   perm        [n_total] int32: perm[i] for i < n = original row of sorted row i; the tail
+ *               perm[n .. n_total) lists the filtered-out rows (only bev_pool_grad_perm reads it)
+ * These calls REQUIRE tables produced by bevb200_bev_pool_prepare_* (intervals tile [0, n) in
+ * ascending rank order); bev_pool_perm relies on that to zero-fill the empty cells in the same
+ * pass.  bev_pool_grad_perm zero-fills the rows of x_grad that were filtered out. */
 BEVB200_API int bevb200_bev_pool_perm(int b, int d, int h, int w, int n, int c, int n_intervals,
                           const float *x, const int32_t *perm, const int32_t *geom_feats,
                           const int32_t *interval_starts, const int32_t *interval_lengths,
