@@ -65,6 +65,18 @@ __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst_smem, const void *src
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
       ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// one elected lane of a fully converged warp (elect.sync): the compiler keeps the tcgen05 issue
+// sequence on the uniform datapath; an `if (lane == 0)` branch instead makes it wrap every
+// UTCHMMA in an ELECT / BRA.U.ANY waterfall loop (measured: ~100 clk per MMA issue)
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
@@ -174,11 +186,21 @@ __global__ void __launch_bounds__(kTcThreads, 2) spconv_tc_kernel_v2(const TcPar
     const uint32_t row_off = (uint32_t)r * 128u;
     // neighbour rows of this tile for every offset, staged once in shared memory
     int32_t *nbr_s = reinterpret_cast<int32_t *>(smem + (size_t)NS * stage_bytes);
-    for (int i = tid; i < p.kvol * kTileM; i += kTcProducerThreads) {
-      const int k = i >> 7, rr = i & 127, o = row0 + rr;
-      int v = o < p.n_out ? __ldg(p.nbr + (long long)k * p.n_out + o) : -1;
-      if (v >= p.n_in) v = -1;
-      nbr_s[i] = v;
+    {
+      // neighbour table of the tile: all (<= 14) loads of a thread are issued before any is used
+      constexpr int kPer = (27 * kTileM + kTcProducerThreads - 1) / kTcProducerThreads;
+      int tv[kPer];
+#pragma unroll
+      for (int u = 0; u < kPer; ++u) {
+        const int i = tid + u * kTcProducerThreads;
+        const int k = i >> 7, rr = i & 127, o = row0 + rr;
+        tv[u] = (i < p.kvol * kTileM && o < p.n_out) ? __ldg(p.nbr + (long long)k * p.n_out + o) : -1;
+      }
+#pragma unroll
+      for (int u = 0; u < kPer; ++u) {
+        const int i = tid + u * kTcProducerThreads;
+        if (i < p.kvol * kTileM) nbr_s[i] = tv[u] >= p.n_in ? -1 : tv[u];
+      }
     }
     asm volatile("bar.sync 1, %0;" ::"n"(kTcProducerThreads) : "memory");
 
@@ -630,6 +652,7 @@ struct TcParamsV4 {
   int nsa, nsb;       // TMEM A-ring stages, smem B-ring stages
   int acc_cols;       // accumulator columns (>= 32)
   int tmem_cols;      // allocation (power of two >= acc_cols + nsa * nsplit * 32)
+  long long *prof;    // optional: per-role cycle counters of CTA 0 (dev profiling)
 };
 
 __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16]) {
@@ -649,8 +672,29 @@ __device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem,
       ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+// 4x4 transpose of float4 registers across the 4 lanes of a quad (lane & 3): after the call
+// a[c] on quad lane i holds what a[i] held on quad lane c.  Two butterfly rounds, 16 SHFL.
+__device__ __forceinline__ float4 shfl_xor_f4(const float4 &v, int m) {
+  float4 r;
+  r.x = __shfl_xor_sync(0xffffffffu, v.x, m);
+  r.y = __shfl_xor_sync(0xffffffffu, v.y, m);
+  r.z = __shfl_xor_sync(0xffffffffu, v.z, m);
+  r.w = __shfl_xor_sync(0xffffffffu, v.w, m);
+  return r;
+}
+__device__ __forceinline__ void quad_transpose(float4 (&a)[4], int lane) {
+  const bool b1 = (lane & 2) != 0, b0 = (lane & 1) != 0;
+  float4 x = b1 ? a[0] : a[2], y = b1 ? a[1] : a[3];
+  x = shfl_xor_f4(x, 2); y = shfl_xor_f4(y, 2);
+  if (b1) { a[0] = x; a[1] = y; } else { a[2] = x; a[3] = y; }
+  x = b0 ? a[0] : a[1]; y = b0 ? a[2] : a[3];
+  x = shfl_xor_f4(x, 1); y = shfl_xor_f4(y, 1);
+  if (b0) { a[0] = x; a[2] = y; } else { a[1] = x; a[3] = y; }
+}
+
 template <int NSPLIT>
 __global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v4(const TcParamsV4 p) {
+  const long long kernel_t0 = clock64();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -669,7 +713,7 @@ __global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v4(const TcPar
 
   if (tid == 0) {
     for (int s = 0; s < p.nsa; ++s) {
-      mbar_init(a_full + 8 * s, kTcProducerThreads);
+      mbar_init(a_full + 8 * s, 8);   // one arrival per producer warp
       mbar_init(a_empty + 8 * s, 1);
     }
     for (int s = 0; s < p.nsb; ++s) {
@@ -696,26 +740,38 @@ __global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v4(const TcPar
     // TMEM lane quarter q = warp & 3 is the only one this warp may touch: row = 32 q + lane
     const int q = warp & 3, half = warp >> 2;
     const int r = q * 32 + lane;
-    for (int i = tid; i < p.kvol * kTileM; i += kTcProducerThreads) {
-      const int k = i >> 7, rr = i & 127, o = row0 + rr;
-      int v = o < p.n_out ? __ldg(p.nbr + (long long)k * p.n_out + o) : -1;
-      if (v >= p.n_in) v = -1;
-      nbr_s[i] = v;
+    {
+      // neighbour table of the tile: all (<= 14) loads of a thread are issued before any is used
+      constexpr int kPer = (27 * kTileM + kTcProducerThreads - 1) / kTcProducerThreads;
+      int tv[kPer];
+#pragma unroll
+      for (int u = 0; u < kPer; ++u) {
+        const int i = tid + u * kTcProducerThreads;
+        const int k = i >> 7, rr = i & 127, o = row0 + rr;
+        tv[u] = (i < p.kvol * kTileM && o < p.n_out) ? __ldg(p.nbr + (long long)k * p.n_out + o) : -1;
+      }
+#pragma unroll
+      for (int u = 0; u < kPer; ++u) {
+        const int i = tid + u * kTcProducerThreads;
+        if (i < p.kvol * kTileM) nbr_s[i] = tv[u] >= p.n_in ? -1 : tv[u];
+      }
     }
     asm volatile("bar.sync 1, %0;" ::"n"(kTcProducerThreads) : "memory");
 
+    // Coalesced gather: load instruction t of a warp covers rows {4j + t : j = 0..7} of its
+    // quarter, 4 lanes x 16 B per row (64 contiguous bytes), so a warp-level LDG.128 touches 8
+    // cache lines instead of 32 (measured: the one-row-per-lane mapping was L1 wavefront bound).
+    // The quad transpose at consume time hands every lane the 64 bytes of ITS row.
     auto issue = [&](int it, float4 (&v)[4]) {
       const int kk = it * kKBlock + half * 16;
       const int k = kk >> p.cin_shift;
-      const int ch = kk & (p.c_in - 1);
-      const int src = k < p.kvol ? nbr_s[k * kTileM + r] : -1;
-      if (src >= 0) {
-        const float4 *g = reinterpret_cast<const float4 *>(p.features + (long long)src * p.c_in + ch);
+      const int ch = (kk & (p.c_in - 1)) + 4 * (lane & 3);
+      const int src_own = k < p.kvol ? nbr_s[k * kTileM + r] : -1;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = __ldg(g + j);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int t = 0; t < 4; ++t) {
+        const int src = __shfl_sync(0xffffffffu, src_own, (lane & ~3) + t);
+        v[t] = src >= 0 ? __ldg(reinterpret_cast<const float4 *>(p.features + (long long)src * p.c_in + ch))
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
     constexpr int PD = 4;
@@ -731,8 +787,12 @@ __global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v4(const TcPar
         if (it < n_iters) {
           const int s = it % p.nsa;
           const uint32_t ph = (uint32_t)(it / p.nsa) & 1u;
-          mbar_wait(a_empty + 8 * s, ph ^ 1u);
+          const long long t0 = clock64();
+          quad_transpose(v[jj], lane);
+          if (lane == 0) mbar_wait(a_empty + 8 * s, ph ^ 1u);   // one poller per warp
+          __syncwarp();
           tc_fence_after();
+          const long long t1 = clock64();
           uint32_t hi[16], lo[16];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -748,14 +808,23 @@ __global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v4(const TcPar
           if (NSPLIT == 2) tc_st16(lane_base + col + 32u, lo);
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
           tc_fence_before();
-          mbar_arrive(a_full + 8 * s);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(a_full + 8 * s);            // 8 arrivals per K block, not 256
+          const long long t2 = clock64();
           if (it + PD < n_iters) issue(it + PD, v[jj]);
+          if (p.prof && blockIdx.x == 0 && tid == 0) {
+            p.prof[0] += t1 - t0;             // transpose + wait for a free TMEM stage
+            p.prof[1] += t2 - t1;             // split + tcgen05.st + wait::st + arrive
+            p.prof[2] += clock64() - t2;      // issue of the next gather loads
+          }
         }
       }
     }
     // =============================== epilogue ============================================
+    const long long e0 = clock64();
     mbar_wait(accbar, 0);
     tc_fence_after();
+    if (p.prof && blockIdx.x == 0 && tid == 0) p.prof[3] += clock64() - e0;   // drain: last MMAs
     const int orow = row0 + q * 32 + lane;
     const int ncol_half = p.c_out / 2;
     const int col_begin = half * ncol_half;
@@ -795,10 +864,14 @@ __global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v4(const TcPar
     const uint32_t idesc = umma_idesc_tf32(kTileM, p.c_out);
     for (int it = 0; it < n_iters; ++it) {
       const int sa = it % p.nsa, sb = it % p.nsb;
+      const long long m0 = clock64();
       mbar_wait(a_full + 8 * sa, (uint32_t)(it / p.nsa) & 1u);
+      const long long m1 = clock64();
       mbar_wait(b_full + 8 * sb, (uint32_t)(it / p.nsb) & 1u);
       tc_fence_after();
-      if (lane == 0) {
+      const long long m2 = clock64();
+      if (p.prof && blockIdx.x == 0 && lane == 0) { p.prof[4] += m1 - m0; p.prof[5] += m2 - m1; }
+      if (elect_one_sync()) {
         const uint32_t a_hi = a_ring + (uint32_t)sa * kAStageCols;   // lane 0, column offset
         const uint32_t a_lo = a_hi + 32u;
         const uint32_t bstage = smem_base + (uint32_t)sb * (uint32_t)b_stage_bytes;
@@ -819,6 +892,7 @@ __global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v4(const TcPar
         tc_commit(a_empty + 8 * sa);
         tc_commit(b_empty + 8 * sb);
         if (it == n_iters - 1) tc_commit(accbar);
+        if (p.prof && blockIdx.x == 0) p.prof[6] += clock64() - m2;   // MMA issue + commits
       }
       __syncwarp();
     }
@@ -838,6 +912,7 @@ __global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v4(const TcPar
   }
   tc_fence_before();
   __syncthreads();
+  if (p.prof && blockIdx.x == 0 && tid == 0) p.prof[7] += clock64() - kernel_t0;   // whole CTA
   if (warp == 8) {
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
@@ -971,6 +1046,15 @@ int spconv_forward_tc(const float *features, const float *weight, const float *p
     p4.out = out; p4.n_in = n_in; p4.n_out = n_out; p4.c_in = c_in; p4.c_out = c_out; p4.kvol = kvol;
     p4.relu = relu; p4.nkb = p.nkb; p4.cin_shift = p.cin_shift; p4.wpacked = p.wpacked;
     p4.acc_cols = p.acc_cols;
+    {
+      // dev profiling: BEVB200_TC_PROF=<device pointer of 8 int64 counters, hex>
+      static long long *prof_ptr = (long long *)-1;
+      if (prof_ptr == (long long *)-1) {
+        const char *e = getenv("BEVB200_TC_PROF");
+        prof_ptr = e ? (long long *)strtoull(e, nullptr, 16) : nullptr;
+      }
+      p4.prof = prof_ptr;
+    }
     // 256 TMEM columns per CTA (two CTAs per SM): accumulator + A ring
     p4.nsa = (256 - p4.acc_cols) / (nsplit * 32);
     if (p4.nsa > 4) p4.nsa = 4;
