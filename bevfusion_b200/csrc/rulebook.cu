@@ -106,19 +106,45 @@ __device__ __forceinline__ bool out_site_of(const int4 c, int k, const ConvGeom 
   return true;
 }
 
-__global__ void rb_mark_outputs_kernel(const int32_t *__restrict__ indices, int n, ConvGeom g,
-                                       uint32_t *__restrict__ bits) {
-  const long long total = (long long)n * g.kvol;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
-       t += (long long)gridDim.x * blockDim.x) {
-    int j = (int)(t / g.kvol), k = (int)(t % g.kvol);
-    int4 c = *reinterpret_cast<const int4 *>(indices + 4ll * j);
+// One thread per input voxel.  Per dimension only the kernel offsets k with
+// (q + pad - k*dil) % stride == 0 reach an output site, so the thread walks the <= prod(ceil(K/s))
+// valid (kx, ky, kz) combinations (8 of 27 for k3 s2) instead of testing all of them.
+template <bool FILL>
+__global__ void rb_conv_sites_kernel(const int32_t *__restrict__ indices, int n, ConvGeom g,
+                                     uint32_t *__restrict__ bits,
+                                     const uint32_t *__restrict__ prefix, int n_out,
+                                     int32_t *__restrict__ nbr) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    const int4 c = *reinterpret_cast<const int4 *>(indices + 4ll * j);
     if ((unsigned)c.x >= (unsigned)g.batch) continue;
-    int p[3];
-    if (!out_site_of(c, k, g, p)) continue;
-    long long s = flat_site(c.x, p[0], p[1], p[2], g.out_shape);
-    uint32_t bit = 1u << (s & 31);
-    if (!(bits[s >> 5] & bit)) atomicOr(bits + (s >> 5), bit);
+    const int q[3] = {c.y, c.z, c.w};
+    for (int kx = 0; kx < g.ksize[0]; ++kx) {
+      int vx = q[0] + g.pad[0] - kx * g.dil[0];
+      if (vx < 0 || vx % g.stride[0]) continue;
+      vx /= g.stride[0];
+      if (vx >= g.out_shape[0]) continue;
+      for (int ky = 0; ky < g.ksize[1]; ++ky) {
+        int vy = q[1] + g.pad[1] - ky * g.dil[1];
+        if (vy < 0 || vy % g.stride[1]) continue;
+        vy /= g.stride[1];
+        if (vy >= g.out_shape[1]) continue;
+        for (int kz = 0; kz < g.ksize[2]; ++kz) {
+          int vz = q[2] + g.pad[2] - kz * g.dil[2];
+          if (vz < 0 || vz % g.stride[2]) continue;
+          vz /= g.stride[2];
+          if (vz >= g.out_shape[2]) continue;
+          const long long s = flat_site(c.x, vx, vy, vz, g.out_shape);
+          if (FILL) {
+            const int k = (kx * g.ksize[1] + ky) * g.ksize[2] + kz;
+            const int o = site_rank(bits, prefix, s);
+            if (o >= 0 && o < n_out) nbr[(long long)k * n_out + o] = j;
+          } else {
+            const uint32_t bit = 1u << (s & 31);
+            if (!(bits[s >> 5] & bit)) atomicOr(bits + (s >> 5), bit);
+          }
+        }
+      }
+    }
   }
 }
 
@@ -141,23 +167,6 @@ __global__ void rb_out_indices_kernel(const uint32_t *__restrict__ bits,
         *reinterpret_cast<int4 *>(out_indices + 4ll * r) = make_int4((int)s, x, y, z);
       ++r;
     }
-  }
-}
-
-__global__ void rb_conv_nbr_kernel(const int32_t *__restrict__ indices, int n, ConvGeom g,
-                                   const uint32_t *__restrict__ bits,
-                                   const uint32_t *__restrict__ prefix, int n_out,
-                                   int32_t *__restrict__ nbr) {
-  const long long total = (long long)n * g.kvol;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
-       t += (long long)gridDim.x * blockDim.x) {
-    int j = (int)(t / g.kvol), k = (int)(t % g.kvol);
-    int4 c = *reinterpret_cast<const int4 *>(indices + 4ll * j);
-    if ((unsigned)c.x >= (unsigned)g.batch) continue;
-    int p[3];
-    if (!out_site_of(c, k, g, p)) continue;
-    int o = site_rank(bits, prefix, flat_site(c.x, p[0], p[1], p[2], g.out_shape));
-    if (o >= 0 && o < n_out) nbr[(long long)k * n_out + o] = j;
   }
 }
 
@@ -301,8 +310,8 @@ int bevb200_rulebook_prepare(const int32_t *indices, int n_in, int batch_size,
   if (subm) {
     BEVB200_LAUNCH(rb_mark_inputs_kernel, grid_for(n_in, 256), 256, 0, st, indices, n_in, g, w.bits);
   } else {
-    BEVB200_LAUNCH(rb_mark_outputs_kernel, grid_for((long long)n_in * g.kvol, 256), 256, 0, st,
-                   indices, n_in, g, w.bits);
+    BEVB200_LAUNCH(rb_conv_sites_kernel<false>, grid_for(n_in, 128), 128, 0, st, indices, n_in, g, w.bits,
+                   (const uint32_t *)nullptr, 0, (int32_t *)nullptr);
   }
   int rc = exclusive_scan_u32(w.bits, w.prefix, w.nwords, w.tiles, w.total, true, st);
   if (rc) return rc;
@@ -341,8 +350,8 @@ int bevb200_rulebook_fill(const int32_t *indices, int n_in, int batch_size,
     BEVB200_CUDA(cudaMemsetAsync(nbr, 0xff, (size_t)g.kvol * n_out * sizeof(int32_t), st));
     BEVB200_LAUNCH(rb_out_indices_kernel, grid_for((long long)w.nwords, 256), 256, 0, st, w.bits,
                    w.prefix, w.nwords, g, n_out, out_indices);
-    BEVB200_LAUNCH(rb_conv_nbr_kernel, grid_for((long long)n_in * g.kvol, 256), 256, 0, st,
-                   indices, n_in, g, w.bits, w.prefix, n_out, nbr);
+    BEVB200_LAUNCH(rb_conv_sites_kernel<true>, grid_for(n_in, 128), 128, 0, st, indices, n_in, g, w.bits,
+                   (const uint32_t *)w.prefix, n_out, nbr);
   }
   return BEVB200_OK;
 }

@@ -77,6 +77,26 @@ __device__ __forceinline__ bool elect_one_sync() {
       : "=r"(pred));
   return pred != 0;
 }
+__device__ __forceinline__ void bulk_copy_g2s_mcast(uint32_t dst_smem, const void *src, uint32_t bytes,
+                                                    uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1], %2, [%3], %4;"
+      ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void tc_commit_mcast(uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
@@ -653,6 +673,7 @@ struct TcParamsV4 {
   int acc_cols;       // accumulator columns (>= 32)
   int tmem_cols;      // allocation (power of two >= acc_cols + nsa * nsplit * 32)
   long long *prof;    // optional: per-role cycle counters of CTA 0 (dev profiling)
+  int csz;            // thread-block cluster size (1, 2 or 4): the weight stages are multicast
 };
 
 __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16]) {
@@ -718,7 +739,7 @@ __global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v4(const TcPar
     }
     for (int s = 0; s < p.nsb; ++s) {
       mbar_init(b_full + 8 * s, 1);
-      mbar_init(b_empty + 8 * s, 1);
+      mbar_init(b_empty + 8 * s, p.csz);   // released by the MMA warp of every CTA of the cluster
     }
     mbar_init(accbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -730,8 +751,10 @@ __global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v4(const TcPar
   }
   tc_fence_before();
   __syncthreads();
+  if (p.csz > 1) cluster_sync_all();      // peers' barriers are initialised before any multicast
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  const uint16_t cmask = (uint16_t)((1u << p.csz) - 1u);
   const uint32_t a_ring = tmem_base + (uint32_t)p.acc_cols;       // column offset of A stage 0
   constexpr uint32_t kAStageCols = NSPLIT * 32;
 
@@ -890,7 +913,7 @@ __global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v4(const TcPar
           }
         }
         tc_commit(a_empty + 8 * sa);
-        tc_commit(b_empty + 8 * sb);
+        if (p.csz > 1) tc_commit_mcast(b_empty + 8 * sb, cmask); else tc_commit(b_empty + 8 * sb);
         if (it == n_iters - 1) tc_commit(accbar);
         if (p.prof && blockIdx.x == 0) p.prof[6] += clock64() - m2;   // MMA issue + commits
       }
@@ -898,20 +921,28 @@ __global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v4(const TcPar
     }
   } else {
     // =============================== weight loader =======================================
+    // With a cluster, CTA rank c fetches slice c of every weight stage from L2 ONCE and multicasts
+    // it into the same ring slot of all CTAs of the cluster (their b_full barriers count the bytes);
+    // a slot is rewritten only after the MMA warps of ALL cluster CTAs released it (b_empty).
     if (lane == 0) {
+      const uint32_t crank = p.csz > 1 ? cluster_ctarank() : 0u;
+      const uint32_t slice = (uint32_t)b_stage_bytes / (uint32_t)p.csz;
       for (int it = 0; it < n_iters; ++it) {
         const int sb = it % p.nsb;
         mbar_wait(b_empty + 8 * sb, ((uint32_t)(it / p.nsb) & 1u) ^ 1u);
         mbar_arrive_expect_tx(b_full + 8 * sb, (uint32_t)b_stage_bytes);
-        bulk_copy_g2s(smem_base + (uint32_t)sb * (uint32_t)b_stage_bytes,
-                      p.wpacked + (long long)it * (long long)(NSPLIT * p.c_out * 32),
-                      (uint32_t)b_stage_bytes, b_full + 8 * sb);
+        const uint32_t dst = smem_base + (uint32_t)sb * (uint32_t)b_stage_bytes + crank * slice;
+        const char *src = reinterpret_cast<const char *>(p.wpacked) +
+                          (long long)it * (long long)b_stage_bytes + crank * slice;
+        if (p.csz > 1) bulk_copy_g2s_mcast(dst, src, slice, b_full + 8 * sb, cmask);
+        else bulk_copy_g2s(dst, src, slice, b_full + 8 * sb);
       }
     }
     __syncwarp();
   }
   tc_fence_before();
   __syncthreads();
+  if (p.csz > 1) cluster_sync_all();      // nobody leaves while a peer may still signal it
   if (p.prof && blockIdx.x == 0 && tid == 0) p.prof[7] += clock64() - kernel_t0;   // whole CTA
   if (warp == 8) {
     __syncwarp();
@@ -1065,16 +1096,41 @@ int spconv_forward_tc(const float *features, const float *weight, const float *p
     if (nsb4 < 2) nsb4 = 2;
     p4.nsb = nsb4;
     const size_t smem4 = (size_t)nsb4 * b_stage4 + nbr4 + 1024;
-    const int grid4 = (n_out + kTileM - 1) / kTileM;
+    // thread-block clusters: the weight stream is the dominant L2 traffic for wide layers
+    // (27*Cin*Cout*8 bytes per 128-row tile); a cluster of 2 halves it
+    static int forced_csz = -1;
+    if (forced_csz < 0) {
+      const char *e = getenv("BEVB200_SPCONV_CLUSTER");
+      forced_csz = e ? atoi(e) : 0;
+    }
+    int csz = forced_csz ? forced_csz : ((long long)c_in * c_out >= 64 * 64 ? 2 : 1);
+    if (csz != 1 && csz != 2 && csz != 4) csz = 1;
+    p4.csz = csz;
+    int grid4 = (n_out + kTileM - 1) / kTileM;
+    grid4 = (grid4 + csz - 1) / csz * csz;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid4);
+    cfg.blockDim = dim3(kV4Threads);
+    cfg.dynamicSmemBytes = smem4;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = csz;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
     if (nsplit == 2) {
       BEVB200_CUDA(cudaFuncSetAttribute(spconv_tc_kernel_v4<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)smem4));
-      BEVB200_LAUNCH(spconv_tc_kernel_v4<2>, grid4, kV4Threads, smem4, st, p4);
+      BEVB200_CUDA(cudaLaunchKernelEx(&cfg, spconv_tc_kernel_v4<2>, p4));
     } else {
       BEVB200_CUDA(cudaFuncSetAttribute(spconv_tc_kernel_v4<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)smem4));
-      BEVB200_LAUNCH(spconv_tc_kernel_v4<1>, grid4, kV4Threads, smem4, st, p4);
+      BEVB200_CUDA(cudaLaunchKernelEx(&cfg, spconv_tc_kernel_v4<1>, p4));
     }
+    ++g_launch_count;
     if (packed) BEVB200_CUDA(cudaFreeAsync(packed, st));
     return BEVB200_OK;
   }

@@ -111,22 +111,27 @@ class SparseConvolution(SparseModule):
         if self.transposed or self.inverse:
             raise NotImplementedError("transposed / inverse sparse conv is outside the hot path")
         indices = input.indices
+        skey = ("__auto__", indices.data_ptr(), indices.shape[0], tuple(input.spatial_shape),
+                tuple(self.kernel_size), tuple(self.stride), tuple(self.padding),
+                tuple(self.dilation), bool(self.subm))
         key = self.indice_key
-        if key is None:
-            key = ("__auto__", indices.data_ptr(), indices.shape[0], tuple(input.spatial_shape),
-                   tuple(self.kernel_size), tuple(self.stride), tuple(self.padding),
-                   tuple(self.dilation), bool(self.subm))
-        datas = input.indice_dict.get(key, None)
+        datas = input.indice_dict.get(key, None) if key is not None else None
+        if datas is None:
+            datas = input.indice_dict.get(skey, None)      # same geometry built under another key
+            if datas is not None and key is not None:
+                input.indice_dict[key] = datas
         if datas is not None:
-            outids, _, rb, _, out_shape = datas[0], datas[1], datas[2], datas[3], datas[5]
-            return rb, out_shape
+            return datas[2], datas[5]
         rb, out_shape = ops.get_rulebook(indices, input.batch_size, input.spatial_shape,
                                          self.kernel_size, self.stride, self.padding,
                                          self.dilation, self.output_padding, self.subm,
                                          self.transposed)
         # (outids, indices, indice_pairs, indice_pair_num, spatial_shape) as conv.py:176-182,
         # with the Rulebook object in the indice_pairs slot, plus the output shape
-        input.indice_dict[key] = (rb.outids, indices, rb, None, input.spatial_shape, out_shape)
+        datas = (rb.outids, indices, rb, None, input.spatial_shape, out_shape)
+        input.indice_dict[skey] = datas
+        if key is not None:
+            input.indice_dict[key] = datas
         return rb, out_shape
 
     def forward(self, input, scale=None, shift=None, residual=None, relu=False, precision=None):
