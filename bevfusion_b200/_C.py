@@ -26,6 +26,7 @@ _SIGNATURES = {
     "bevb200_bev_pool_grad": (c_int, [c_int] * 7 + [_P] * 6),
     "bevb200_bev_pool_perm": (c_int, [c_int] * 7 + [_P] * 7 + [c_size_t, _P]),
     "bevb200_bev_pool_grad_perm": (c_int, [c_int] * 8 + [_P] * 7),
+    "bevb200_bev_pool_lift": (c_int, [c_int] * 7 + [_P, _P, c_int, c_int] + [_P] * 6 + [c_size_t, _P]),
     "bevb200_bev_pool_prepare_workspace_bytes": (c_size_t, [c_int]),
     "bevb200_bev_pool_prepare_geom": (c_int, [_P, c_int, c_int, _P, _P, _P, c_int] + [_P] * 7
                                       + [c_size_t, _P]),
@@ -45,6 +46,9 @@ _SIGNATURES = {
     "bevb200_spconv_packed_weight_bytes": (c_size_t, [c_int] * 4),
     "bevb200_spconv_pack_weights": (c_int, [_P] + [c_int] * 4 + [_P, _P]),
     "bevb200_spconv_forward_packed": (c_int, [_P, _P, _P] + [c_int] * 5 + [_P, _P, _P, c_int, c_int, _P, _P]),
+    "bevb200_rulebook_transpose": (c_int, [_P, c_int, c_int, c_int, _P, _P]),
+    "bevb200_spconv_backward_workspace_bytes": (c_size_t, [c_int] * 3),
+    "bevb200_spconv_backward": (c_int, [_P] * 5 + [c_int] * 6 + [_P, _P, _P, c_size_t, _P]),
     "bevb200_sparse_to_dense": (c_int, [_P, _P, c_int, c_int, c_int, _P, c_int, _P, _P]),
 }
 

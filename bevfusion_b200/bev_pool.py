@@ -237,6 +237,29 @@ class BEVPoolPlan:
         c = x.shape[-1]
         return _PoolPerm.apply(x.reshape(-1, c).contiguous(), self.tables)
 
+    def lift_pool(self, depth, ctx):
+        """Fused LSS lift + pool (inference): `depth` [B, N, D, fH, fW] softmax volume and `ctx`
+        [B, N, fH, fW, C] channels-last context features -> raw op output [B, nz, nx, ny, C], equal
+        to pool(depth.unsqueeze(-1) * ctx.unsqueeze(2)) without materialising that volume
+        (lss.py:68-73 / depth_lss.py:92-97 followed by base.py:141-176)."""
+        _C.require_cuda(depth, "depth", torch.float32)
+        _C.require_cuda(ctx, "ctx", torch.float32)
+        B, N, D, fH, fW = depth.shape
+        c = ctx.shape[-1]
+        assert tuple(ctx.shape) == (B, N, fH, fW, c)
+        t = self.tables
+        assert depth.numel() == t.n_total
+        Bq, Dq, Hq, Wq = t.dims
+        with torch.cuda.device(depth.device):
+            out = torch.empty((Bq, Dq, Hq, Wq, c), dtype=torch.float32, device=depth.device)
+            ws = _ws(_C.lib().bevb200_bev_pool_workspace_bytes(t.n_kept, c), depth.device)
+            rc = _C.lib().bevb200_bev_pool_lift(
+                Bq, Dq, Hq, Wq, t.n_kept, c, t.n_intervals, _C.ptr(depth), _C.ptr(ctx), D, fH * fW,
+                _C.ptr(t.perm), _C.ptr(t.geom), _C.ptr(t.starts), _C.ptr(t.lengths), _C.ptr(out),
+                _C.ptr(ws), ws.numel(), _C.current_stream(depth.device))
+        _C.check(rc, "bev_pool_lift")
+        return out
+
     def __call__(self, x):
         out = self.pool(x)                                  # [B, Z, X, Y, C]
         out = out.permute(0, 4, 1, 2, 3).contiguous()       # bev_pool.py:97

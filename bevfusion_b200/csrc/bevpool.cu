@@ -246,15 +246,23 @@ __global__ void pool_interval_cells_kernel(const int32_t *__restrict__ geom_feat
   }
 }
 
-template <int Q, bool PERM>
+// MODE 0: rows already sorted (one TMA bulk copy per stage); MODE 1: rows gathered through perm;
+// MODE 2: fused LSS lift -- row r is depth[perm[r]] * ctx[pixel(perm[r]), :] and is never materialised
+// (x = ctx [n_pix, C] channels-last, `depth` = flattened [B*N, D, fH*fW] softmax volume).
+struct LiftDims {
+  int d_bins, hw;   // depth bins D and fH*fW: original index i -> pixel row (i / (D*hw)) * hw + i % hw
+};
+template <int Q, int MODE>
 __global__ void __launch_bounds__(256)
     bevpool_fwd_tma_kernel(const float4 *__restrict__ x, const int32_t *__restrict__ perm,
+                           const float *__restrict__ depth, LiftDims lift,
                            const int32_t *__restrict__ starts, const int32_t *__restrict__ cells,
                            int n, int n_intervals, int rows_per_warp, int zfill, int total_cells,
                            float4 *__restrict__ out, float4 *__restrict__ partial) {
   constexpr int QPL = (Q + 31) / 32;              // float4 columns per lane
   constexpr uint32_t kRowBytes = Q * 16;
-  constexpr uint32_t kStageBytes = kStageRows * kRowBytes;
+  constexpr bool PERM = MODE != 0;
+  constexpr uint32_t kStageBytes = kStageRows * kRowBytes + (MODE == 2 ? 128u : 0u);   // + 32 depth values
   extern __shared__ __align__(128) uint8_t pool_smem[];
   __shared__ uint64_t bars[8 * kPoolStages];
   const int warp = threadIdx.x >> 5, lane = lane_id(), nwarps = blockDim.x >> 5;
@@ -285,7 +293,14 @@ __global__ void __launch_bounds__(256)
     const int nrows = min(kStageRows, R1 - r0s);
     const uint32_t dst = my_u32 + (uint32_t)s * kStageBytes;
     if constexpr (PERM) {
-      const long long prow = lane < nrows ? (long long)__ldg(perm + r0s + lane) : 0ll;
+      long long prow = lane < nrows ? (long long)__ldg(perm + r0s + lane) : 0ll;
+      if constexpr (MODE == 2) {
+        if (lane < nrows)   // the row's depth weight, staged behind the 32 feature rows
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + kStageRows * kRowBytes + (uint32_t)lane * 4u),
+                       "l"(depth + prow) : "memory");
+        const long long per_cam = (long long)lift.d_bins * lift.hw;
+        prow = (prow / per_cam) * lift.hw + prow % lift.hw;     // pixel row of ctx
+      }
 #pragma unroll
       for (int t = 0; t < Q; ++t) {
         const int f = lane + 32 * t;
@@ -381,6 +396,7 @@ __global__ void __launch_bounds__(256)
       pool_mbar_wait(bar0 + 8 * s, (uint32_t)(it / kPoolStages) & 1u);
     }
     const float4 *rows = reinterpret_cast<const float4 *>(my + (size_t)s * kStageBytes);
+    const float *dvals = reinterpret_cast<const float *>(my + (size_t)s * kStageBytes + kStageRows * kRowBytes);
     int row = 0, iv = 0;   // iv = how many boundaries of this stage have been consumed
     while (row < nrows) {
       const uint32_t m = mask >> row;
@@ -405,10 +421,19 @@ __global__ void __launch_bounds__(256)
           if (q < Q) {
             const float4 a = rows[(rr + 0) * Q + q], b = rows[(rr + 1) * Q + q];
             const float4 c = rows[(rr + 2) * Q + q], d = rows[(rr + 3) * Q + q];
+            if constexpr (MODE == 2) {
+              const float wa = dvals[rr], wb = dvals[rr + 1], wc = dvals[rr + 2], wd = dvals[rr + 3];
+              // same arithmetic as the unfused path: product rounded to fp32, then added
+              acc[u].x += __fmul_rn(wa, a.x); acc[u].y += __fmul_rn(wa, a.y); acc[u].z += __fmul_rn(wa, a.z); acc[u].w += __fmul_rn(wa, a.w);
+              acc[u].x += __fmul_rn(wb, b.x); acc[u].y += __fmul_rn(wb, b.y); acc[u].z += __fmul_rn(wb, b.z); acc[u].w += __fmul_rn(wb, b.w);
+              acc[u].x += __fmul_rn(wc, c.x); acc[u].y += __fmul_rn(wc, c.y); acc[u].z += __fmul_rn(wc, c.z); acc[u].w += __fmul_rn(wc, c.w);
+              acc[u].x += __fmul_rn(wd, d.x); acc[u].y += __fmul_rn(wd, d.y); acc[u].z += __fmul_rn(wd, d.z); acc[u].w += __fmul_rn(wd, d.w);
+            } else {
             acc[u].x += a.x; acc[u].y += a.y; acc[u].z += a.z; acc[u].w += a.w;
             acc[u].x += b.x; acc[u].y += b.y; acc[u].z += b.z; acc[u].w += b.w;
             acc[u].x += c.x; acc[u].y += c.y; acc[u].z += c.z; acc[u].w += c.w;
             acc[u].x += d.x; acc[u].y += d.y; acc[u].z += d.z; acc[u].w += d.w;
+            }
           }
         }
       }
@@ -418,7 +443,12 @@ __global__ void __launch_bounds__(256)
           const int q = lane + 32 * u;
           if (q < Q) {
             const float4 a = rows[rr * Q + q];
+            if constexpr (MODE == 2) {
+              const float wa = dvals[rr];
+              acc[u].x += __fmul_rn(wa, a.x); acc[u].y += __fmul_rn(wa, a.y); acc[u].z += __fmul_rn(wa, a.z); acc[u].w += __fmul_rn(wa, a.w);
+            } else {
             acc[u].x += a.x; acc[u].y += a.y; acc[u].z += a.z; acc[u].w += a.w;
+            }
           }
         }
       }
@@ -618,14 +648,15 @@ static int launch_fwd(const float *x, const int32_t *perm, const int32_t *geom,
 template <int Q>
 static int launch_fwd_tma(const float *x, const int32_t *perm, const int32_t *geom,
                           const int32_t *starts, int n, int c, int n_intervals, PoolDims dm, float *out,
-                          void *ws, int zfill, cudaStream_t st) {
+                          void *ws, int zfill, cudaStream_t st, const float *depth = nullptr,
+                          LiftDims lift = LiftDims{1, 1}) {
   size_t nchunks = ((size_t)n + kChunkRows - 1) / kChunkRows;
   if (nchunks < (size_t)kTmaMaxRanges) nchunks = kTmaMaxRanges;
   float *partial = (float *)ws;
   int32_t *cells = (int32_t *)((char *)ws + align_up(2 * nchunks * (size_t)c * sizeof(float)));
   BEVB200_LAUNCH(pool_interval_cells_kernel, grid_for(n_intervals, 256), 256, 0, st, geom, starts, n,
                  n_intervals, dm, cells);
-  const size_t stage_bytes = (size_t)kStageRows * Q * 16;
+  const size_t stage_bytes = (size_t)kStageRows * Q * 16 + (depth ? 128 : 0);
   int warps = (int)((200 * 1024) / (kPoolStages * stage_bytes));
   if (warps > 8) warps = 8;
   if (warps < 1) warps = 1;
@@ -635,19 +666,18 @@ static int launch_fwd_tma(const float *x, const int32_t *perm, const int32_t *ge
   rpw = (rpw + kStageRows - 1) / kStageRows * kStageRows;
   const int n_ranges = (n + rpw - 1) / rpw;
   const int grid = (n_ranges + warps - 1) / warps;
-  if (perm) {
-    BEVB200_CUDA(cudaFuncSetAttribute(bevpool_fwd_tma_kernel<Q, true>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    BEVB200_LAUNCH((bevpool_fwd_tma_kernel<Q, true>), grid, warps * 32, smem, st, (const float4 *)x, perm,
-                   starts, cells, n, n_intervals, rpw, zfill, dm.b * dm.d * dm.h * dm.w, (float4 *)out,
-                   (float4 *)partial);
-  } else {
-    BEVB200_CUDA(cudaFuncSetAttribute(bevpool_fwd_tma_kernel<Q, false>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    BEVB200_LAUNCH((bevpool_fwd_tma_kernel<Q, false>), grid, warps * 32, smem, st, (const float4 *)x, perm,
-                   starts, cells, n, n_intervals, rpw, zfill, dm.b * dm.d * dm.h * dm.w, (float4 *)out,
-                   (float4 *)partial);
-  }
+#define BEVB200_POOL_TMA_LAUNCH(MODE)                                                             \
+  do {                                                                                              \
+    BEVB200_CUDA(cudaFuncSetAttribute(bevpool_fwd_tma_kernel<Q, MODE>,                              \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+    BEVB200_LAUNCH((bevpool_fwd_tma_kernel<Q, MODE>), grid, warps * 32, smem, st, (const float4 *)x, \
+                   perm, depth, lift, starts, cells, n, n_intervals, rpw, zfill,                     \
+                   dm.b * dm.d * dm.h * dm.w, (float4 *)out, (float4 *)partial);                     \
+  } while (0)
+  if (depth) BEVB200_POOL_TMA_LAUNCH(2);
+  else if (perm) BEVB200_POOL_TMA_LAUNCH(1);
+  else BEVB200_POOL_TMA_LAUNCH(0);
+#undef BEVB200_POOL_TMA_LAUNCH
   BEVB200_LAUNCH((bevpool_fwd_tma_fixup_kernel<Q>), (n_ranges * 32 + 255) / 256, 256, 0, st, starts, cells, n,
                  n_intervals, rpw, n_ranges, (float4 *)out, (const float4 *)partial);
   return BEVB200_OK;
@@ -950,6 +980,35 @@ int bevb200_bev_pool_grad_perm(int b, int d, int h, int w, int n, int n_total, i
   BEVB200_REQUIRE(perm != nullptr || n_total == 0, "null perm");
   return pool_backward(b, d, h, w, n, n_total, c, n_intervals, out_grad, perm, geom_feats,
                        interval_starts, interval_lengths, x_grad, stream);
+}
+
+int bevb200_bev_pool_lift(int b, int d, int h, int w, int n, int c, int n_intervals, const float *depth,
+                          const float *ctx, int depth_bins, int pixels_per_camera, const int32_t *perm,
+                          const int32_t *geom_feats, const int32_t *interval_starts,
+                          const int32_t *interval_lengths, float *out, void *workspace,
+                          size_t workspace_bytes, void *stream) {
+  (void)interval_lengths;
+  BEVB200_REQUIRE(b > 0 && d > 0 && h > 0 && w > 0 && c > 0 && n >= 0 && n_intervals >= 0, "bad sizes");
+  BEVB200_REQUIRE(out != nullptr, "null out");
+  BEVB200_REQUIRE(depth_bins > 0 && pixels_per_camera > 0, "bad lift dims");
+  BEVB200_REQUIRE((long long)b * d * h * w < (1ll << 31), "grid has too many cells");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int zfill = (b * d == 1 && n > 0 && n_intervals > 0) ? 1 : 0;
+  if (!zfill) BEVB200_CUDA(cudaMemsetAsync(out, 0, (size_t)b * d * h * w * c * sizeof(float), st));
+  if (n == 0 || n_intervals == 0) return BEVB200_OK;
+  BEVB200_REQUIRE(depth && ctx && perm && geom_feats && interval_starts, "null input");
+  BEVB200_REQUIRE(((uintptr_t)ctx % 16 == 0) && ((uintptr_t)out % 16 == 0), "ctx / out must be 16-byte aligned");
+  if (workspace == nullptr || workspace_bytes < pool_partial_bytes(n, c)) {
+    snprintf(g_last_error, sizeof(g_last_error), "bev_pool_lift: workspace too small");
+    return BEVB200_EWORKSPACE;
+  }
+  PoolDims dm{b, d, h, w};
+  LiftDims lift{depth_bins, pixels_per_camera};
+#define CALL_LIFT(Q, G) return launch_fwd_tma<Q>(ctx, perm, geom_feats, interval_starts, n, c, n_intervals, dm, \
+                                                 out, workspace, zfill, st, depth, lift)
+  BEVB200_POOL_DISPATCH(c, CALL_LIFT, BEVB200_REQUIRE(false, "bev_pool_lift: channel count not in {16,32,64,80,96,128,160,256}"));
+#undef CALL_LIFT
+  return BEVB200_OK;
 }
 
 size_t bevb200_bev_pool_prepare_workspace_bytes(int n_total) {

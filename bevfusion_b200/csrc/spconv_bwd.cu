@@ -1,0 +1,183 @@
+// Sparse convolution backward (fp32) for sm_100a.
+//
+// Replaces spconv::indiceConvBackward<float> (spconv_ops.h:363-456): per kernel offset the
+// reference gathers features and out-grad rows, runs two cuBLAS GEMMs (filtersGrad[k] = in^T dout,
+// inBuf = dout W[k]^T) and scatter-adds inBuf into inputGrad.  Here:
+//   * input gradient  = ONE implicit-GEMM launch of the forward kernel on the transposed
+//     neighbour table (nbrT[k, j] = output row fed by input row j through offset k) with the
+//     per-offset transposed weights:  dIn[j] = sum_k dOut[nbrT[k, j]] @ W[k]^T
+//   * weight gradient = one kernel: CTA (offset k, chunk of output rows) accumulates the
+//     Cin x Cout outer-product sum of its chunk in registers and adds it to dW[k] with fp32
+//     atomics (the chunk partition is fixed; only the order of ~n_out/2048 adds per element varies).
+#include "common.cuh"
+
+namespace bevb200 {
+
+int spconv_forward_simt(const float *features, const float *weight, const int32_t *nbr, int n_in,
+                        int n_out, int c_in, int c_out, int kvol, const float *scale,
+                        const float *shift, const float *residual, int relu, float *out,
+                        cudaStream_t st);
+int spconv_forward_tc(const float *features, const float *weight, const float *packed,
+                      const int32_t *nbr, int n_in, int n_out, int c_in, int c_out, int kvol,
+                      const float *scale, const float *shift, const float *residual, int relu,
+                      int precision, float *out, cudaStream_t st);
+
+__global__ void nbr_transpose_kernel(const int32_t *__restrict__ nbr, int kvol, int n_out, int n_in,
+                                     int32_t *__restrict__ nbr_t) {
+  const long long total = (long long)kvol * n_out;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(t / n_out), o = (int)(t % n_out);
+    const int j = nbr[t];
+    if (j >= 0 && j < n_in) nbr_t[(long long)k * n_in + j] = o;   // unique writer per (k, j)
+  }
+}
+
+__global__ void weight_transpose_kernel(const float *__restrict__ w, int kvol, int c_in, int c_out,
+                                        float *__restrict__ wt) {
+  const long long total = (long long)kvol * c_in * c_out;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(t % c_out), ci = (int)((t / c_out) % c_in), k = (int)(t / ((long long)c_out * c_in));
+    wt[((long long)k * c_out + co) * c_in + ci] = w[t];
+  }
+}
+
+// dW[k][ci][co] += sum over output rows o of the chunk with j = nbr[k, o] >= 0 of f[j][ci] * g[o][co]
+constexpr int kWgChunk = 2048;   // output rows per CTA
+constexpr int kWgStep = 16;      // rows staged per step
+template <int TCI, int TCO>     // per-thread micro-tile; 256 threads cover (16*TCI) x (16*TCO)
+__global__ void __launch_bounds__(256)
+    spconv_wgrad_kernel(const float *__restrict__ features, const float *__restrict__ out_grad,
+                        const int32_t *__restrict__ nbr, int n_in, int n_out, int c_in, int c_out,
+                        float *__restrict__ w_grad) {
+  constexpr int BCI = 16 * TCI, BCO = 16 * TCO;
+  __shared__ float fs[kWgStep][BCI + 1];
+  __shared__ float gs[kWgStep][BCO + 1];
+  __shared__ int js[kWgStep];
+  const int k = blockIdx.y;
+  const int o_begin = blockIdx.x * kWgChunk, o_end = min(n_out, o_begin + kWgChunk);
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  for (int ci0 = 0; ci0 < c_in; ci0 += BCI) {
+    for (int co0 = 0; co0 < c_out; co0 += BCO) {
+      float acc[TCI][TCO];
+#pragma unroll
+      for (int a = 0; a < TCI; ++a)
+#pragma unroll
+        for (int b = 0; b < TCO; ++b) acc[a][b] = 0.f;
+      for (int o0 = o_begin; o0 < o_end; o0 += kWgStep) {
+        if (tid < kWgStep) {
+          const int o = o0 + tid;
+          int j = o < o_end ? __ldg(nbr + (long long)k * n_out + o) : -1;
+          js[tid] = (j >= 0 && j < n_in) ? j : -1;
+        }
+        __syncthreads();
+        for (int e = tid; e < kWgStep * BCI; e += 256) {
+          const int r = e / BCI, c = e % BCI, j = js[r];
+          fs[r][c] = (j >= 0 && ci0 + c < c_in) ? __ldg(features + (long long)j * c_in + ci0 + c) : 0.f;
+        }
+        for (int e = tid; e < kWgStep * BCO; e += 256) {
+          const int r = e / BCO, c = e % BCO, o = o0 + r;
+          gs[r][c] = (js[r] >= 0 && co0 + c < c_out) ? __ldg(out_grad + (long long)o * c_out + co0 + c) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < kWgStep; ++r) {
+          float fa[TCI], gb[TCO];
+#pragma unroll
+          for (int a = 0; a < TCI; ++a) fa[a] = fs[r][ty * TCI + a];
+#pragma unroll
+          for (int b = 0; b < TCO; ++b) gb[b] = gs[r][tx * TCO + b];
+#pragma unroll
+          for (int a = 0; a < TCI; ++a)
+#pragma unroll
+            for (int b = 0; b < TCO; ++b) acc[a][b] = fmaf(fa[a], gb[b], acc[a][b]);
+        }
+        __syncthreads();
+      }
+#pragma unroll
+      for (int a = 0; a < TCI; ++a)
+#pragma unroll
+        for (int b = 0; b < TCO; ++b) {
+          const int ci = ci0 + ty * TCI + a, co = co0 + tx * TCO + b;
+          if (ci < c_in && co < c_out && acc[a][b] != 0.f)
+            atomicAdd(w_grad + ((long long)k * c_in + ci) * c_out + co, acc[a][b]);
+        }
+    }
+  }
+}
+
+}  // namespace bevb200
+
+using namespace bevb200;
+
+extern "C" {
+
+int bevb200_rulebook_transpose(const int32_t *nbr, int kernel_volume, int n_out, int n_in,
+                               int32_t *nbr_t, void *stream) {
+  BEVB200_REQUIRE(kernel_volume > 0 && n_out >= 0 && n_in >= 0, "bad sizes");
+  if (n_in == 0) return BEVB200_OK;
+  BEVB200_REQUIRE(nbr_t != nullptr, "null nbr_t");
+  cudaStream_t st = (cudaStream_t)stream;
+  BEVB200_CUDA(cudaMemsetAsync(nbr_t, 0xff, (size_t)kernel_volume * n_in * sizeof(int32_t), st));
+  if (n_out == 0) return BEVB200_OK;
+  BEVB200_REQUIRE(nbr != nullptr, "null nbr");
+  BEVB200_LAUNCH(nbr_transpose_kernel, grid_for((long long)kernel_volume * n_out, 256), 256, 0, st, nbr,
+                 kernel_volume, n_out, n_in, nbr_t);
+  return BEVB200_OK;
+}
+
+size_t bevb200_spconv_backward_workspace_bytes(int c_in, int c_out, int kernel_volume) {
+  if (c_in <= 0 || c_out <= 0 || kernel_volume <= 0) return 0;
+  return align_up((size_t)kernel_volume * c_in * c_out * sizeof(float));
+}
+
+int bevb200_spconv_backward(const float *features, const float *weight, const float *out_grad,
+                            const int32_t *nbr, const int32_t *nbr_t, int n_in, int n_out, int c_in,
+                            int c_out, int kernel_volume, int precision, float *input_grad,
+                            float *weight_grad, void *workspace, size_t workspace_bytes,
+                            void *stream) {
+  BEVB200_REQUIRE(n_in >= 0 && n_out >= 0 && c_in > 0 && c_out > 0 && kernel_volume > 0, "bad sizes");
+  BEVB200_REQUIRE(weight && weight_grad, "null weight");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t wbytes = (size_t)kernel_volume * c_in * c_out * sizeof(float);
+  BEVB200_CUDA(cudaMemsetAsync(weight_grad, 0, wbytes, st));
+  if (n_in == 0) return BEVB200_OK;
+  BEVB200_REQUIRE(input_grad != nullptr, "null input_grad");
+  if (n_out == 0) {
+    BEVB200_CUDA(cudaMemsetAsync(input_grad, 0, (size_t)n_in * c_in * sizeof(float), st));
+    return BEVB200_OK;
+  }
+  BEVB200_REQUIRE(features && out_grad && nbr && nbr_t, "null argument");
+  if (workspace == nullptr || workspace_bytes < bevb200_spconv_backward_workspace_bytes(c_in, c_out, kernel_volume)) {
+    snprintf(g_last_error, sizeof(g_last_error), "spconv_backward: workspace too small");
+    return BEVB200_EWORKSPACE;
+  }
+  // dIn = sparse_conv(dOut, W^T, nbrT)
+  float *wt = (float *)workspace;
+  BEVB200_LAUNCH(weight_transpose_kernel, grid_for((long long)kernel_volume * c_in * c_out, 256), 256, 0,
+                 st, weight, kernel_volume, c_in, c_out, wt);
+  int rc;
+  if (precision == BEVB200_PREC_FP32)
+    rc = spconv_forward_simt(out_grad, wt, nbr_t, n_out, n_in, c_out, c_in, kernel_volume, nullptr,
+                             nullptr, nullptr, 0, input_grad, st);
+  else
+    rc = spconv_forward_tc(out_grad, wt, nullptr, nbr_t, n_out, n_in, c_out, c_in, kernel_volume, nullptr,
+                           nullptr, nullptr, 0, precision, input_grad, st);
+  if (rc) return rc;
+  // dW
+  dim3 grid((n_out + kWgChunk - 1) / kWgChunk, kernel_volume);
+  if (c_in >= 64 && c_out >= 64) {
+    BEVB200_LAUNCH((spconv_wgrad_kernel<4, 4>), grid, 256, 0, st, features, out_grad, nbr, n_in, n_out,
+                   c_in, c_out, weight_grad);
+  } else if (c_in >= 32 && c_out >= 32) {
+    BEVB200_LAUNCH((spconv_wgrad_kernel<2, 2>), grid, 256, 0, st, features, out_grad, nbr, n_in, n_out,
+                   c_in, c_out, weight_grad);
+  } else {
+    BEVB200_LAUNCH((spconv_wgrad_kernel<1, 1>), grid, 256, 0, st, features, out_grad, nbr, n_in, n_out,
+                   c_in, c_out, weight_grad);
+  }
+  return BEVB200_OK;
+}
+
+}  // extern "C"

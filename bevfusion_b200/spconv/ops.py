@@ -229,9 +229,61 @@ def indice_conv(features, filters, indice_pairs, indice_pair_num, num_activate_o
                        precision=precision)
 
 
+def transpose_nbr(nbr, n_in):
+    """nbr [K, n_out] -> nbr_t [K, n_in]: nbr_t[k, j] = output row fed by input row j through k."""
+    _C.require_cuda(nbr, "nbr", torch.int32)
+    kvol, n_out = nbr.shape
+    dev = nbr.device
+    with torch.cuda.device(dev):
+        nbr_t = torch.empty((kvol, int(n_in)), dtype=torch.int32, device=dev)
+        rc = _C.lib().bevb200_rulebook_transpose(_C.ptr(nbr), kvol, n_out, int(n_in), _C.ptr(nbr_t),
+                                                 _C.current_stream(dev))
+    _C.check(rc, "rulebook_transpose")
+    return nbr_t
+
+
+def sparse_conv_backward(features, weight, out_grad, nbr, nbr_t=None, precision=None):
+    """(input_grad [n_in, Cin], weight_grad like `weight`) of out = sparse_conv(features, weight, nbr)."""
+    _C.require_cuda(features, "features", torch.float32)
+    _C.require_cuda(weight, "weight", torch.float32)
+    _C.require_cuda(out_grad, "out_grad", torch.float32)
+    n_in, c_in = features.shape
+    c_out = weight.shape[-1]
+    kvol, n_out = nbr.shape
+    assert tuple(out_grad.shape) == (n_out, c_out)
+    if nbr_t is None:
+        nbr_t = transpose_nbr(nbr, n_in)
+    if precision is None:
+        precision = default_precision()
+    dev = features.device
+    L = _C.lib()
+    with torch.cuda.device(dev):
+        din = torch.empty((n_in, c_in), dtype=torch.float32, device=dev)
+        dw = torch.empty_like(weight)
+        ws = torch.empty(max(L.bevb200_spconv_backward_workspace_bytes(c_in, c_out, kvol), 256),
+                         dtype=torch.uint8, device=dev)
+        rc = L.bevb200_spconv_backward(_C.ptr(features), _C.ptr(weight), _C.ptr(out_grad), _C.ptr(nbr),
+                                       _C.ptr(nbr_t), n_in, n_out, c_in, c_out, kvol, int(precision),
+                                       _C.ptr(din), _C.ptr(dw), _C.ptr(ws), ws.numel(),
+                                       _C.current_stream(dev))
+    _C.check(rc, "spconv_backward")
+    return din, dw
+
+
 def indice_conv_backward(features, filters, out_bp, indice_pairs, indice_pair_num, inverse=False,
-                         subm=False):
-    raise NotImplementedError("sparse conv backward is not built yet (SURVEY.md section 8, a18)")
+                         subm=False, precision=None):
+    """Drop-in for ops.indice_conv_backward (ops.py:177-189): returns [input_grad, filters_grad].
+    `indice_pairs` may be the reference [K, 2, N] tensor or a Rulebook."""
+    if filters.dtype != torch.float32:
+        raise NotImplementedError("only fp32 filters are implemented")
+    if isinstance(indice_pairs, Rulebook):
+        assert not inverse
+        nbr = indice_pairs.nbr
+    else:
+        nbr = nbr_from_pairs(indice_pairs, indice_pair_num, out_bp.shape[0], inverse)
+    din, dw = sparse_conv_backward(features.contiguous(), filters.contiguous(), out_bp.contiguous(), nbr,
+                                   precision=precision)
+    return [din, dw]
 
 
 class _SparseConvExt:
@@ -250,6 +302,11 @@ class _SparseConvExt:
                          inverse, subm):
         return indice_conv(features, filters, indice_pairs, indice_pair_num, num_activate_out,
                            bool(inverse), bool(subm))
+
+    @staticmethod
+    def indice_conv_backward_fp32(features, filters, out_bp, indice_pairs, indice_pair_num, inverse, subm):
+        return indice_conv_backward(features, filters, out_bp, indice_pairs, indice_pair_num,
+                                    bool(inverse), bool(subm))
 
     def __getattr__(self, name):
         raise NotImplementedError("sparse_conv_ext.%s is outside the hot path" % name)

@@ -98,6 +98,22 @@ BEVB200_API int bevb200_bev_pool_grad_perm(int b, int d, int h, int w, int n, in
                                const int32_t *geom_feats, const int32_t *interval_starts,
                                const int32_t *interval_lengths, float *x_grad, void *stream);
 
+/* Fused LSS lift + pool ("next" row (f)1 of SURVEY.md section 8; BEVPoolv2-style): the lifted volume
+ * x[p, :] = depth[p] * ctx[pixel(p), :] of LSSTransform / DepthLSSTransform.get_cam_feats
+ * (mmdet3d/models/vtransforms/lss.py:68-73, depth_lss.py:92-97) is never materialised; the pooling
+ * kernel gathers the (L2-resident) context row and the depth weight of every kept frustum point:
+ *     out[cell] = sum_{p in cell} fp32(depth[p] * ctx[pixel(p), :])
+ *   depth  [n_total] fp32 = softmax depth volume flattened as [B*N, D, fH*fW]
+ *   ctx    [B*N*fH*fW, c] fp32, channels-last context features
+ *   original point index i -> pixel row (i / (depth_bins*pixels_per_camera)) * pixels_per_camera
+ *                                       + i % pixels_per_camera
+ * Tables as for bevb200_bev_pool_perm (from bevb200_bev_pool_prepare_geom).  Forward only. */
+BEVB200_API int bevb200_bev_pool_lift(int b, int d, int h, int w, int n, int c, int n_intervals,
+                          const float *depth, const float *ctx, int depth_bins,
+                          int pixels_per_camera, const int32_t *perm, const int32_t *geom_feats,
+                          const int32_t *interval_starts, const int32_t *interval_lengths,
+                          float *out, void *workspace, size_t workspace_bytes, void *stream);
+
 /* bev_pool precompute.  Replaces, on device and in one call, the index glue of
  * BaseTransform.bev_pool (mmdet3d/models/vtransforms/base.py:149-169: quantise, batch
  * index, bounds mask), bev_pool() (ops/bev_pool/bev_pool.py:87-94: rank, argsort,
@@ -258,6 +274,24 @@ BEVB200_API int bevb200_spconv_forward_packed(const float *features, const float
                                   int kernel_volume, const float *scale, const float *shift,
                                   const float *residual, int relu, int precision, float *out,
                                   void *stream);
+
+/* Sparse convolution backward.  Replaces spconv::indiceConvBackward<float> (spconv_ops.h:363-456;
+ * bound as sparse_conv_ext.indice_conv_backward_fp32):
+ *     input_grad[j, :]  = sum_k out_grad[nbr_t[k, j], :] @ weight[k]^T     [n_in, c_in]
+ *     weight_grad[k]    = sum_o features[nbr[k, o], :]^T (x) out_grad[o, :] [K, c_in, c_out]
+ * nbr_t [K, n_in] is the transposed neighbour table from bevb200_rulebook_transpose()
+ * (nbr_t[k, j] = the output row that input row j feeds through offset k, or -1).
+ * The input gradient runs the forward implicit-GEMM kernel on (out_grad, W^T, nbr_t) in the
+ * requested precision; the weight gradient accumulates fixed 2048-row chunks with fp32 atomics.
+ * workspace: bevb200_spconv_backward_workspace_bytes() (the transposed weights). */
+BEVB200_API int bevb200_rulebook_transpose(const int32_t *nbr, int kernel_volume, int n_out, int n_in,
+                               int32_t *nbr_t, void *stream);
+BEVB200_API size_t bevb200_spconv_backward_workspace_bytes(int c_in, int c_out, int kernel_volume);
+BEVB200_API int bevb200_spconv_backward(const float *features, const float *weight, const float *out_grad,
+                            const int32_t *nbr, const int32_t *nbr_t, int n_in, int n_out, int c_in,
+                            int c_out, int kernel_volume, int precision, float *input_grad,
+                            float *weight_grad, void *workspace, size_t workspace_bytes,
+                            void *stream);
 
 /* SparseConvTensor.dense() (structure.py:49-59) fused with SparseEncoder's
  * permute(0,1,4,2,3).view(N, C*D, H, W) (sparse_encoder.py:126-130):

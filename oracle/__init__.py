@@ -227,6 +227,24 @@ def indice_conv(features, filters, indice_pairs, indice_num, num_act_out, invers
     return out
 
 
+def indice_conv_backward(features, filters, out_bp, indice_pairs, indice_num, inverse=False):
+    """indiceConvBackward<float>, spconv_ops.h:363-456 -> (input_grad [N,Cin], filters_grad
+    [K,Cin,Cout]) in float64 arithmetic: per offset k and pair (in, out):
+    filters_grad[k] += f[in]^T (x) g[out];  input_grad[in] += g[out] @ W[k]^T."""
+    f, g = features.astype(np.float64), out_bp.astype(np.float64)
+    w = filters.reshape(-1, filters.shape[-2], filters.shape[-1]).astype(np.float64)
+    din = np.zeros_like(f)
+    dw = np.zeros_like(w)
+    for k in range(w.shape[0]):
+        n = int(indice_num[k])
+        if n <= 0:
+            continue
+        a, b = indice_pairs[k, 1 if inverse else 0, :n], indice_pairs[k, 0 if inverse else 1, :n]
+        dw[k] = f[a].T @ g[b]
+        np.add.at(din, a, g[b] @ w[k].T)
+    return din.astype(np.float32), dw.reshape(filters.shape).astype(np.float32)
+
+
 def flat_index(outids, out_shape):
     """((b*X + x)*Y + y)*Z + z -- the order of the reference GPU rulebook (indice.cu.h:59-60)."""
     o = outids.astype(np.int64)

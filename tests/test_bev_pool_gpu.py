@@ -208,3 +208,30 @@ def test_plan_full_size_c2_properties(cuda):
     assert torch.equal(gflat[perm], w.reshape(-1, 80)[cell])
     dropped = t.perm[t.n_kept:].long()
     assert float(gflat[dropped].abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("cfg_name", ["tiny", "C2"])
+def test_fused_lift_pool(cuda, cfg_name):
+    """fused LSS lift + pool == pool(depth (x) ctx) without the materialised volume."""
+    from bevfusion_b200 import synthetic as S
+    from bevfusion_b200.bev_pool import BEVPoolPlan
+    geom, cfg = S.camera_geometry(cfg_name, device=cuda)
+    plan = BEVPoolPlan(geom, cfg["xbound"], cfg["ybound"], cfg["zbound"])
+    B, N, D, fH, fW, _ = geom.shape
+    C = cfg["C"]
+    g = torch.Generator(device=cuda).manual_seed(1)
+    depth = torch.softmax(torch.randn(B, N, D, fH, fW, generator=g, device=cuda), dim=2).contiguous()
+    ctx = torch.randn(B, N, fH, fW, C, generator=g, device=cuda)
+    x = depth.unsqueeze(-1) * ctx.unsqueeze(2)                  # [B, N, D, fH, fW, C]  (the reference's lift)
+    gold = plan.pool(x)
+    out = plan.lift_pool(depth, ctx)
+    scale = float(gold.abs().max())
+    assert float((out - gold).abs().max()) <= 1e-6 * scale
+    # and against a float64 scatter-add of the lifted volume
+    t = plan.tables
+    perm = t.perm[:t.n_kept].long()
+    nxy = int(plan.nx[0]) * int(plan.nx[1])
+    cell = t.geom[:, 0].long() * int(plan.nx[1]) + t.geom[:, 1].long()
+    ref = torch.zeros(nxy, C, dtype=torch.float64, device=cuda)
+    ref.index_add_(0, cell, x.reshape(-1, C)[perm].double())
+    assert float((out.reshape(-1, C).double() - ref).abs().max()) <= 1e-4 * float(ref.abs().max())
