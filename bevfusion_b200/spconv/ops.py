@@ -218,13 +218,20 @@ def indice_conv(features, filters, indice_pairs, indice_pair_num, num_activate_o
                 subm=False, precision=None):
     """Drop-in for ops.indice_conv (ops.py:128-152).  `indice_pairs` may be the reference
     [K, 2, N] tensor (converted to a neighbour table first) or a Rulebook."""
-    if filters.dtype != torch.float32:
-        raise NotImplementedError("only fp32 filters are implemented (indice_conv_half: next)")
+    if filters.dtype not in (torch.float32, torch.half):
+        raise NotImplementedError("filters must be fp32 or fp16")
     if isinstance(indice_pairs, Rulebook):
         assert not inverse
         nbr = indice_pairs.nbr
     else:
         nbr = nbr_from_pairs(indice_pairs, indice_pair_num, num_activate_out, inverse)
+    if filters.dtype == torch.half or features.dtype == torch.half:
+        # indice_conv_half (ops.py:141-150): the reference runs HGEMMs; here half tensors are
+        # widened, the conv accumulates in fp32 on the tensor cores, and the result is narrowed
+        # once -- at least as accurate as the reference's fp16 path
+        out = sparse_conv(features.float().contiguous(), filters.float().contiguous(), nbr,
+                          int(num_activate_out), precision=precision)
+        return out.half()
     return sparse_conv(features.contiguous(), filters.contiguous(), nbr, int(num_activate_out),
                        precision=precision)
 
@@ -299,6 +306,12 @@ class _SparseConvExt:
 
     @staticmethod
     def indice_conv_fp32(features, filters, indice_pairs, indice_pair_num, num_activate_out,
+                         inverse, subm):
+        return indice_conv(features, filters, indice_pairs, indice_pair_num, num_activate_out,
+                           bool(inverse), bool(subm))
+
+    @staticmethod
+    def indice_conv_half(features, filters, indice_pairs, indice_pair_num, num_activate_out,
                          inverse, subm):
         return indice_conv(features, filters, indice_pairs, indice_pair_num, num_activate_out,
                            bool(inverse), bool(subm))

@@ -235,3 +235,41 @@ def test_fused_lift_pool(cuda, cfg_name):
     ref = torch.zeros(nxy, C, dtype=torch.float64, device=cuda)
     ref.index_add_(0, cell, x.reshape(-1, C)[perm].double())
     assert float((out.reshape(-1, C).double() - ref).abs().max()) <= 1e-4 * float(ref.abs().max())
+
+
+def test_stress_c5_properties(cuda):
+    """BASELINE config C5 (6 cam 512x1408 -> 64x176 features, D=200, C=80, 256x256 BEV:
+    N' = 13.5 M rows, x = 4.3 GB): size-independent properties of the plan path at full size."""
+    from bevfusion_b200 import synthetic as S
+    from bevfusion_b200.bev_pool import BEVPoolPlan
+    geom, cfg = S.camera_geometry("C5", device=cuda)
+    assert geom.shape[2] == 200 or geom.shape[2] == len(np.arange(*cfg["dbound"]))
+    plan = BEVPoolPlan(geom, cfg["xbound"], cfg["ybound"], cfg["zbound"])
+    t = plan.tables
+    n_total = geom.numel() // 3
+    assert t.n_total == n_total
+    del geom
+    # table invariants: perm is a permutation, intervals tile [0, n_kept), ranks ascend strictly per interval
+    perm = t.perm.long()
+    seen = torch.zeros(n_total, dtype=torch.bool, device=cuda)
+    seen[perm] = True
+    assert bool(seen.all())
+    assert int(t.lengths.sum()) == t.n_kept and int(t.starts[0]) == 0
+    assert bool((t.starts[1:] - t.starts[:-1] == t.lengths[:-1]).all())
+    rk = t.ranks[:t.n_kept]
+    assert bool((rk[1:] >= rk[:-1]).all())
+    assert bool((rk[t.starts[1:].long()] > rk[t.starts[1:].long() - 1]).all())
+    # pooling a volume of ones counts the points of every cell (exact in fp32: counts < 2^24)
+    C = 80
+    x = torch.ones((n_total, C), device=cuda)
+    out = plan.pool(x)                                        # [1, 1, 256, 256, 80]
+    counts = torch.zeros(256 * 256, dtype=torch.float32, device=cuda)
+    cell = t.geom[:, 0].long() * 256 + t.geom[:, 1].long()
+    counts.index_add_(0, cell[t.starts.long()], t.lengths.float())
+    assert torch.equal(out.reshape(-1, C)[:, 0], counts) and torch.equal(out.reshape(-1, C)[:, 79], counts)
+    assert int(t.lengths.max()) > 1000                       # very long intervals exist at this size
+    # mass conservation on random data
+    x.normal_()
+    out = plan.pool(x)
+    kept_sum = x[perm[:t.n_kept]].double().sum()
+    assert abs(float(out.double().sum() - kept_sum)) <= 1e-6 * float(x[perm[:t.n_kept]].double().abs().sum())

@@ -344,3 +344,21 @@ def test_module_autograd(cuda):
     assert rel_err(conv1.weight.grad.cpu().numpy(), dw1) <= 1e-4
     assert rel_err(feat.grad.cpu().numpy(), d0) <= 1e-4
     assert rel_err(conv2.bias.grad.cpu().numpy(), w.sum(0).cpu().numpy()) <= 1e-5
+
+
+def test_half_features(cuda):
+    """indice_conv_half: fp16 features / filters in, fp16 out, fp32 accumulation inside."""
+    from bevfusion_b200.spconv import ops
+    ks, st, pd, subm = GEOMS["subm_k3"]
+    shape, B, n, cin, cout = [24, 20, 9], 1, 2000, 32, 32
+    idx = random_sparse(n, shape, B, seed=12)
+    rng = np.random.default_rng(13)
+    feat = rng.standard_normal((n, cin)).astype(np.float16)
+    W = (rng.standard_normal((*ks, cin, cout)) / 17).astype(np.float16)
+    gold, _, _ = oracle.sparse_conv(feat.astype(np.float32), idx, B, shape, W.astype(np.float32), ks, st, pd,
+                                    [1, 1, 1], subm)
+    outids, pairs, num = ops.get_indice_pairs(torch.from_numpy(idx).to(cuda), B, shape, ks, st, pd, 1, 0, subm)
+    out = ops.sparse_conv_ext.indice_conv_half(torch.from_numpy(feat).to(cuda), torch.from_numpy(W).to(cuda),
+                                               pairs, num, outids.shape[0], 0, int(subm))
+    assert out.dtype == torch.half
+    assert rel_err(out.float().cpu().numpy(), gold) <= 2e-3      # one fp16 rounding of the result

@@ -113,3 +113,34 @@ def test_vs_reference_cuda_kernel(cuda):
     assert m == mv
     ours = run_ours(cuda, pts, L["voxel_size"], L["point_cloud_range"], mp, mv)
     assert_same(ours, (voxels[:m].cpu().numpy(), coors[:m].cpu().numpy(), num[:m].cpu().numpy(), m))
+
+
+def test_stress_c5_voxel_grid(cuda):
+    """BASELINE config C5 LiDAR side: 0.05 m voxels -> grid 2160x2160x40; bit-exact vs the oracle,
+    and the SubM / strided rulebooks on the 2160x2160x41 grid keep their invariants."""
+    from bevfusion_b200 import synthetic as S
+    from bevfusion_b200.spconv import ops
+    from bevfusion_b200.voxelize import voxelize_mean
+    pts = S.lidar_cloud(seed=2)
+    vs, cr = [0.05, 0.05, 0.2], [-54.0, -54.0, -5.0, 54.0, 54.0, 3.0]
+    gold = oracle.hard_voxelize(pts, vs, cr, 10, 300000)
+    ours = run_ours(cuda, pts, vs, cr, 10, 300000)
+    assert_same(ours, gold)
+    v, c, n = (torch.from_numpy(a).to(cuda) for a in ours)
+    feats, coords = voxelize_mean(v, c, n, 0)
+    shape = [2160, 2160, 41]
+    rb, _ = ops.get_rulebook(coords, 1, shape, 3, 1, 1, 1, 0, True)
+    nbr = rb.nbr
+    assert bool((nbr[13] == torch.arange(coords.shape[0], device=cuda, dtype=torch.int32)).all())   # centre tap = identity
+    # SubM symmetry: j = nbr[k, i]  <=>  i = nbr[26 - k, j]
+    k = 5
+    i = torch.nonzero(nbr[k] >= 0).squeeze(1)
+    j = nbr[k][i].long()
+    assert bool((nbr[26 - k][j] == i.int()).all())
+    rb2, oshape = ops.get_rulebook(coords, 1, shape, 3, 2, 1, 1, 0, False)
+    assert oshape == [1080, 1080, 21]
+    flat = oracle.flat_index(rb2.outids.cpu().numpy(), oshape)
+    assert np.all(np.diff(flat) > 0)                         # ascending, unique output sites
+    # every input feeds exactly one output through its parity-compatible offsets: pair count check
+    pairs = int((rb2.nbr >= 0).sum())
+    assert pairs >= coords.shape[0] and pairs <= 8 * coords.shape[0]
