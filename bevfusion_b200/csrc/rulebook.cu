@@ -88,24 +88,6 @@ __global__ void rb_subm_nbr_kernel(const int32_t *__restrict__ indices, int n, C
 // ---- strided (regular) sparse conv ----------------------------------------------------
 // output site reached from input site q through kernel offset k: p = (q + pad - k*dil) / stride
 // (exists iff divisible and inside the output grid) -- the set getValidOutPos enumerates.
-__device__ __forceinline__ bool out_site_of(const int4 c, int k, const ConvGeom &g, int p[3]) {
-  int kk[3];
-  kk[2] = k % g.ksize[2];
-  kk[1] = (k / g.ksize[2]) % g.ksize[1];
-  kk[0] = k / (g.ksize[2] * g.ksize[1]);
-  const int q[3] = {c.y, c.z, c.w};
-#pragma unroll
-  for (int d = 0; d < 3; ++d) {
-    int v = q[d] + g.pad[d] - kk[d] * g.dil[d];
-    if (v < 0) return false;
-    if (v % g.stride[d] != 0) return false;
-    v /= g.stride[d];
-    if (v >= g.out_shape[d]) return false;
-    p[d] = v;
-  }
-  return true;
-}
-
 // One thread per input voxel.  Per dimension only the kernel offsets k with
 // (q + pad - k*dil) % stride == 0 reach an output site, so the thread walks the <= prod(ceil(K/s))
 // valid (kx, ky, kz) combinations (8 of 27 for k3 s2) instead of testing all of them.

@@ -2,28 +2,33 @@
 //
 //   out[o, :] = epilogue( sum_k features[nbr[k, o], :] @ W[k] )          (spconv_ops.h:260-361)
 //
-// One CTA owns 128 output rows (UMMA M = 128, cta_group::1) and all Cout <= 128 columns; the
-// fp32 accumulator lives in TMEM (128 lanes x Cout columns) across all kernel offsets and
-// Cin blocks, so every output row is written exactly once, after the fused BN / residual /
-// ReLU epilogue.  Pipeline (NS stages, mbarrier full/empty pairs):
+// One CTA owns 128 output rows (UMMA M = 128, cta_group::1) and all Cout <= 128 columns; the fp32
+// accumulator lives in TMEM across all kernel offsets, so every output row is written exactly
+// once, after the fused BN / residual / ReLU epilogue.  The GEMM K axis is the concatenation over
+// the kernel offsets of the Cin channels, cut into blocks of 32 floats (one 128-byte swizzle row).
 //
-//   warps 0-7  producers: thread (row r, half h) gathers 64 B of features[nbr[k, row0+r]]
-//              (one 32-float K block = 128 B per row per stage) with 16-byte loads, splits every
-//              value into tf32 hi + lo parts (3xTF32: a = hi + lo, hi = a & ~0x1fff) and stores both
-//              into shared memory in the UMMA canonical K-major SWIZZLE_128B layout
-//              (16-byte chunk index XOR (row & 7)).  Missing neighbours become zero rows.
-//              Thread 0 also issues ONE cp.async.bulk (TMA 1-D) per stage for the weights of
-//              (offset k, K block): they are pre-packed in global memory as the exact swizzled
-//              shared-memory image [hi | lo][Cout rows][128 B].
-//   warp 8     lane 0 issues tcgen05.mma.kind::tf32 (M128 x N=Cout x K8): per K step
-//              hi*hi + hi*lo + lo*hi (fp32 accumulate in TMEM) and tcgen05.commit's the stage
-//              back to the producers; after the last stage it commits to the epilogue barrier.
-//   epilogue   warps 0-7 read the accumulator with tcgen05.ld (32 lanes x 16 columns per
-//              instruction; warps w and w+4 share TMEM lane quarter w and split the columns),
-//              apply scale/shift (folded BatchNorm1d), residual and ReLU, and store the row.
+// Default kernel (spconv_tc_kernel_v4, two CTAs per SM, 10 warps each):
+//   warps 0-7  producers: gather the neighbour feature rows with coalesced 16-byte loads (4 lanes
+//              per row; quad-transposed with shuffles so that lane == row), split every value
+//              into tf32 hi + lo (3xTF32: a = hi + lo, hi = a & ~0x1fff) in registers and write
+//              both parts into TENSOR MEMORY with tcgen05.st (A ring of 2-3 stages, 4 K blocks
+//              prefetched in registers).  Missing neighbours become zero rows.
+//   warp 8     one elected lane issues tcgen05.mma.kind::tf32 with A from TMEM and B from shared
+//              memory (M128 x N=Cout x K8; per K step lo*hi + hi*lo + hi*hi, fp32 accumulate),
+//              tcgen05.commit's the A / B ring slots back and finally the accumulator.
+//   warp 9     streams the weights: they are pre-packed in global memory as the exact K-major
+//              SWIZZLE_128B shared-memory image [hi | lo][Cout][128 B] per K block and fetched with
+//              one cp.async.bulk (TMA 1-D) per stage into an up-to-8-deep ring (optionally
+//              multicast across a thread-block cluster).
+//   epilogue   warps 0-7 read the accumulator(s) with tcgen05.ld (32 lanes x 16 columns; warps w
+//              and w+4 share TMEM lane quarter w and split the columns), apply scale / shift
+//              (folded BatchNorm1d), residual and ReLU, and store the row.
+// spconv_tc_kernel_v2 (both operands in shared memory, producers write the swizzled A tile) is
+// the previous generation, kept behind BEVB200_SPCONV_TC_VARIANT=2: ncu showed it shared-memory
+// bound (every M128 MMA re-reads its 4 KB A tile from smem), which is what moved A into TMEM.
 //
-// BEVB200_PREC_TF32X3 keeps fp32-class accuracy (error ~2^-21 per product) at 3 MMAs per K
-// step; BEVB200_PREC_TF32 issues only hi*hi (single-pass TF32, ~1e-3 relative).
+// BEVB200_PREC_TF32X3 keeps fp32-class accuracy (measured 1e-6 .. 1e-5 relative) at 3 MMAs per K
+// step; BEVB200_PREC_TF32 issues only hi*hi (single-pass TF32, ~8e-4 relative).
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -366,288 +371,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) spconv_tc_kernel_v2(const TcPar
   }
 }
 
-// ---- v3: persistent, warp-specialised, separate weight ring, double-buffered accumulator ----
-struct TcParams {
-  const float *features;
-  const float *wpacked;   // [nkb][nsplit][Cout][32] floats, swizzled smem image
-  const int32_t *nbr;
-  const float *scale, *shift, *residual;
-  float *out;
-  int n_in, n_out, c_in, c_out, kvol, relu;
-  int nkb;        // K blocks of 32 floats over the concatenated (offset, channel) axis
-  int cin_shift;  // log2(c_in): c_in is a power of two >= 16 on this path
-  int nsa, nsb;   // depth of the A (gathered features) and B (weights) rings
-  int acc_cols;   // TMEM columns of one accumulator (>= 32); two are allocated
-  int num_tiles;
-};
-
-// Warp roles of the persistent kernel (448 threads, one CTA per SM):
-//   0-7   A producers   gather feature rows -> tf32 hi/lo split -> swizzled smem (A ring)
-//   8     MMA issuer    lane 0 issues tcgen05.mma, commits ring slots / accumulators
-//   9     B loader      lane 0 streams the packed weights with cp.async.bulk (B ring)
-//   10-13 epilogue      tcgen05.ld the finished accumulator, BN/residual/ReLU, store
-// The accumulator is double buffered in TMEM, so the epilogue of tile i overlaps the main loop
-// of tile i+1; the A and B rings run continuously across tile boundaries.
-constexpr int kTcWarpsProducer = 8;
-constexpr int kTcWarpMma = 8, kTcWarpB = 9, kTcWarpEpi0 = 10;
-constexpr int kTcThreadsV3 = 14 * 32;
 constexpr int kMaxStages = 8;
-
-template <int NSPLIT>
-__global__ void __launch_bounds__(kTcThreadsV3, 1) spconv_tc_kernel(const TcParams p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B atoms
-  uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
-  const int a_stage_bytes = NSPLIT * kABlockBytes;
-  const int b_part_bytes = p.c_out * 128;                               // Cout rows x 128 B
-  const int b_stage_bytes = NSPLIT * b_part_bytes;
-  const uint32_t a_ring = smem_base;
-  const uint32_t b_ring = a_ring + (uint32_t)(p.nsa * a_stage_bytes);
-  int32_t *nbr_s = reinterpret_cast<int32_t *>(smem + (size_t)p.nsa * a_stage_bytes +
-                                               (size_t)p.nsb * b_stage_bytes);   // [2][kvol][128]
-  __shared__ uint64_t bars[4 * kMaxStages + 4];
-  __shared__ uint32_t tmem_base_s;
-  const uint32_t a_full = smem_u32(&bars[0]), a_empty = smem_u32(&bars[kMaxStages]);
-  const uint32_t b_full = smem_u32(&bars[2 * kMaxStages]), b_empty = smem_u32(&bars[3 * kMaxStages]);
-  const uint32_t acc_full = smem_u32(&bars[4 * kMaxStages]), acc_empty = smem_u32(&bars[4 * kMaxStages + 2]);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nkb = p.nkb;
-
-  if (tid == 0) {
-    for (int s = 0; s < p.nsa; ++s) {
-      mbar_init(a_full + 8 * s, kTcProducerThreads);
-      mbar_init(a_empty + 8 * s, 1);
-    }
-    for (int s = 0; s < p.nsb; ++s) {
-      mbar_init(b_full + 8 * s, 1);
-      mbar_init(b_empty + 8 * s, 1);
-    }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(acc_full + 8 * b, 1);
-      mbar_init(acc_empty + 8 * b, 128);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == kTcWarpMma) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                 ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)(2 * p.acc_cols)) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = tmem_base_s;
-
-  if (warp < kTcWarpsProducer) {
-    // =============================== A producers =========================================
-    const int r = tid & 127, half = tid >> 7;
-    const uint32_t sw = (uint32_t)(r & 7);
-    const uint32_t row_off = (uint32_t)r * 128u;
-    const int nbr_elems = p.kvol * kTileM;            // per tile
-    constexpr int kNbrPerThread = (27 * kTileM + kTcProducerThreads - 1) / kTcProducerThreads;  // 14
-
-    auto load_nbr = [&](int tile, int i) -> int {     // element i of the tile's [kvol][128] table
-      const int k = i >> 7, rr = i & 127, o = tile * kTileM + rr;
-      int v = (tile < p.num_tiles && o < p.n_out) ? __ldg(p.nbr + (long long)k * p.n_out + o) : -1;
-      return v >= p.n_in ? -1 : v;
-    };
-    // first tile's table straight to smem buffer 0
-    for (int i = tid; i < nbr_elems; i += kTcProducerThreads) nbr_s[i] = load_nbr(blockIdx.x, i);
-    asm volatile("bar.sync 1, %0;" ::"n"(kTcProducerThreads) : "memory");
-
-    // concatenated-K block `it` of tile-local index covers K indices [32*it, 32*it+32); this
-    // thread owns 16 of them (4 float4), inside ONE kernel offset because c_in % 16 == 0
-    auto issue = [&](const int32_t *tbl, int it, float4 (&v)[4]) {
-      const int kk = it * kKBlock + half * 16;
-      const int k = kk >> p.cin_shift;
-      const int ch = kk & (p.c_in - 1);
-      const int src = k < p.kvol ? tbl[k * kTileM + r] : -1;
-      if (src >= 0) {
-        const float4 *q = reinterpret_cast<const float4 *>(p.features + (long long)src * p.c_in + ch);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = __ldg(q + j);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    };
-    constexpr int PD = 4;  // register prefetch distance (K blocks in flight per thread)
-    float4 v[PD][4];
-    // the CTA's K-block stream: g = local_tile * nkb + it
-    const int my_tiles = blockIdx.x < p.num_tiles ? (p.num_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
-    const long long g_total = (long long)my_tiles * nkb;
-    auto issue_g = [&](long long g, float4 (&vv)[4]) {
-      const int lt = (int)(g / nkb), it = (int)(g - (long long)lt * nkb);
-      issue(nbr_s + (lt & 1) * nbr_elems, it, vv);
-    };
-#pragma unroll
-    for (int j = 0; j < PD; ++j)
-      if (j < g_total && j < nkb) issue_g(j, v[j]);   // only the first tile's table is staged yet
-    int nxt[kNbrPerThread];
-    for (long long g0 = 0; g0 < g_total; g0 += PD) {
-#pragma unroll
-      for (int jj = 0; jj < PD; ++jj) {
-        const long long g = g0 + jj;
-        if (g < g_total) {
-          const int lt = (int)(g / nkb), it = (int)(g - (long long)lt * nkb);
-          const int next_tile = blockIdx.x + (lt + 1) * gridDim.x;
-          if (it == 0) {
-            // fetch the NEXT tile's neighbour table into registers (lands in smem mid-tile)
-#pragma unroll
-            for (int u = 0; u < kNbrPerThread; ++u) {
-              const int i = tid + u * kTcProducerThreads;
-              nxt[u] = i < nbr_elems ? load_nbr(next_tile, i) : -1;
-            }
-          }
-          if (it == nkb / 2) {
-            int32_t *dstt = nbr_s + ((lt + 1) & 1) * nbr_elems;
-#pragma unroll
-            for (int u = 0; u < kNbrPerThread; ++u) {
-              const int i = tid + u * kTcProducerThreads;
-              if (i < nbr_elems) dstt[i] = nxt[u];
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(kTcProducerThreads) : "memory");
-          }
-          const int s = (int)(g % p.nsa);
-          const uint32_t ph = (uint32_t)(g / p.nsa) & 1u;
-          mbar_wait(a_empty + 8 * s, ph ^ 1u);
-          const uint32_t stage = a_ring + (uint32_t)s * (uint32_t)a_stage_bytes;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t chunk = (uint32_t)(half * 4 + j);
-            const uint32_t off = row_off + ((chunk ^ sw) << 4);
-            uint4 hi;
-            hi.x = __float_as_uint(v[jj][j].x) & 0xffffe000u;
-            hi.y = __float_as_uint(v[jj][j].y) & 0xffffe000u;
-            hi.z = __float_as_uint(v[jj][j].z) & 0xffffe000u;
-            hi.w = __float_as_uint(v[jj][j].w) & 0xffffe000u;
-            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(stage + off), "r"(hi.x), "r"(hi.y),
-                         "r"(hi.z), "r"(hi.w) : "memory");
-            if (NSPLIT == 2) {
-              float4 lo;
-              lo.x = v[jj][j].x - __uint_as_float(hi.x);
-              lo.y = v[jj][j].y - __uint_as_float(hi.y);
-              lo.z = v[jj][j].z - __uint_as_float(hi.z);
-              lo.w = v[jj][j].w - __uint_as_float(hi.w);
-              asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stage + kABlockBytes + off),
-                           "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
-            }
-          }
-          fence_proxy_async();     // generic-proxy stores -> visible to the tensor core (async proxy)
-          mbar_arrive(a_full + 8 * s);
-          // prefetch PD blocks ahead; the next tile's table is in smem once it >= nkb/2 of this
-          // tile, and PD <= nkb - nkb/2 always holds (nkb >= 12 on this path)
-          if (g + PD < g_total) issue_g(g + PD, v[jj]);
-        }
-      }
-    }
-  } else if (warp == kTcWarpMma) {
-    // =============================== MMA issuer ==========================================
-    const uint32_t idesc = umma_idesc_tf32(kTileM, p.c_out);
-    long long g = 0;
-    int lt = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
-      const int ab = lt & 1;
-      mbar_wait(acc_empty + 8 * ab, ((uint32_t)(lt >> 1) & 1u) ^ 1u);   // epilogue drained this buffer
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(ab * p.acc_cols);
-      for (int it = 0; it < nkb; ++it, ++g) {
-        const int sa = (int)(g % p.nsa), sb = (int)(g % p.nsb);
-        mbar_wait(a_full + 8 * sa, (uint32_t)(g / p.nsa) & 1u);
-        mbar_wait(b_full + 8 * sb, (uint32_t)(g / p.nsb) & 1u);
-        tc_fence_after();
-        if (lane == 0) {
-          const uint32_t astage = a_ring + (uint32_t)sa * (uint32_t)a_stage_bytes;
-          const uint32_t bstage = b_ring + (uint32_t)sb * (uint32_t)b_stage_bytes;
-          const uint64_t a_hi = umma_desc_sw128(astage);
-          const uint64_t a_lo = umma_desc_sw128(astage + kABlockBytes);
-          const uint64_t b_hi = umma_desc_sw128(bstage);
-          const uint64_t b_lo = umma_desc_sw128(bstage + b_part_bytes);
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t adv = (uint64_t)(ks * 2);  // +32 B along K inside the 128-byte swizzle row
-            if (NSPLIT == 2) {
-              tc_mma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, (it > 0 || ks > 0) ? 1u : 0u);
-              tc_mma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
-              tc_mma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
-            } else {
-              tc_mma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, (it > 0 || ks > 0) ? 1u : 0u);
-            }
-          }
-          tc_commit(a_empty + 8 * sa);
-          tc_commit(b_empty + 8 * sb);
-          if (it == nkb - 1) tc_commit(acc_full + 8 * ab);
-        }
-        __syncwarp();
-      }
-    }
-  } else if (warp == kTcWarpB) {
-    // =============================== B loader ============================================
-    if (lane == 0) {
-      long long g = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        for (int it = 0; it < nkb; ++it, ++g) {
-          const int sb = (int)(g % p.nsb);
-          mbar_wait(b_empty + 8 * sb, ((uint32_t)(g / p.nsb) & 1u) ^ 1u);
-          mbar_arrive_expect_tx(b_full + 8 * sb, (uint32_t)b_stage_bytes);
-          bulk_copy_g2s(b_ring + (uint32_t)sb * (uint32_t)b_stage_bytes,
-                        p.wpacked + (long long)it * (long long)(NSPLIT * p.c_out * 32),
-                        (uint32_t)b_stage_bytes, b_full + 8 * sb);
-        }
-      }
-    }
-    __syncwarp();
-  } else {
-    // =============================== epilogue warps ======================================
-    const int q = warp & 3;                           // TMEM lane quarter this warp may access
-    int lt = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
-      const int ab = lt & 1;
-      mbar_wait(acc_full + 8 * ab, (uint32_t)(lt >> 1) & 1u);
-      tc_fence_after();
-      const int orow = tile * kTileM + q * 32 + lane;  // accumulator lane == output row of the tile
-      const uint32_t t_addr = tmem_base + (uint32_t)(ab * p.acc_cols) + ((uint32_t)(q * 32) << 16);
-      for (int c0 = 0; c0 < p.c_out; c0 += 16) {
-        float acc[16];
-        tc_ld16(t_addr + (uint32_t)c0, acc);
-        if (orow < p.n_out) {
-          float *dst = p.out + (long long)orow * p.c_out + c0;
-          const float *res = p.residual ? p.residual + (long long)orow * p.c_out + c0 : nullptr;
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            float y[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float t = acc[j + e];
-              if (p.scale) t *= __ldg(p.scale + c0 + j + e);
-              if (p.shift) t += __ldg(p.shift + c0 + j + e);
-              y[e] = t;
-            }
-            if (res) {
-              const float4 rv = __ldg(reinterpret_cast<const float4 *>(res + j));
-              y[0] += rv.x; y[1] += rv.y; y[2] += rv.z; y[3] += rv.w;
-            }
-            if (p.relu) {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) y[e] = fmaxf(y[e], 0.f);
-            }
-            *reinterpret_cast<float4 *>(dst + j) = make_float4(y[0], y[1], y[2], y[3]);
-          }
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(acc_empty + 8 * ab);                 // this thread is done with the TMEM buffer
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == kTcWarpMma) {
-    __syncwarp();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"((uint32_t)(2 * p.acc_cols)) : "memory");
-  }
-}
 
 // ---- v4: A operand in TENSOR MEMORY (tcgen05.mma TS form) ------------------------------------
 // Measured on v2: with both operands in shared memory the M128 x N x K8 tf32 MMA re-reads the
@@ -674,6 +398,7 @@ struct TcParamsV4 {
   int tmem_cols;      // allocation (power of two >= acc_cols + nsa * nsplit * 32)
   long long *prof;    // optional: per-role cycle counters of CTA 0 (dev profiling)
   int csz;            // thread-block cluster size (1, 2 or 4): the weight stages are multicast
+  int nacc;           // independent TMEM accumulators (1, 2 or 4), summed in the epilogue
 };
 
 __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16]) {
@@ -755,7 +480,7 @@ __global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v4(const TcPar
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   const uint16_t cmask = (uint16_t)((1u << p.csz) - 1u);
-  const uint32_t a_ring = tmem_base + (uint32_t)p.acc_cols;       // column offset of A stage 0
+  const uint32_t a_ring = tmem_base + (uint32_t)(p.nacc * p.acc_cols);   // column offset of A stage 0
   constexpr uint32_t kAStageCols = NSPLIT * 32;
 
   if (warp < 8) {
@@ -854,6 +579,12 @@ __global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v4(const TcPar
     for (int c0 = col_begin; c0 < col_begin + ncol_half; c0 += 16) {
       float acc[16];
       tc_ld16(tmem_base + lane_base + (uint32_t)c0, acc);
+      for (int ai = 1; ai < p.nacc; ++ai) {
+        float more[16];
+        tc_ld16(tmem_base + lane_base + (uint32_t)(ai * p.acc_cols + c0), more);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) acc[e] += more[e];
+      }
       if (orow < p.n_out) {
         float *dst = p.out + (long long)orow * p.c_out + c0;
         const float *res = p.residual ? p.residual + (long long)orow * p.c_out + c0 : nullptr;
@@ -904,12 +635,18 @@ __global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v4(const TcPar
         for (int ks = 0; ks < 4; ++ks) {
           const uint64_t badv = (uint64_t)(ks * 2);   // +32 B along K inside the swizzled row
           const uint32_t aadv = (uint32_t)(ks * 8);   // +8 tf32 = 8 TMEM columns
+          // consecutive MMAs into ONE accumulator serialise at ~64 clk each whatever N is
+          // (measured: 12 MMAs = ~780 clk for N = 16 .. 64); K step ks therefore accumulates into
+          // accumulator ks % nacc, the chains overlap in the tensor pipe, the epilogue adds them
+          const int ai = ks & (p.nacc - 1);
+          const uint32_t d = tmem_base + (uint32_t)(ai * p.acc_cols);
+          const uint32_t first = (it == 0 && ks < p.nacc) ? 0u : 1u;
           if (NSPLIT == 2) {
-            tc_mma_tf32_ts(tmem_base, a_lo + aadv, b_hi + badv, idesc, (it > 0 || ks > 0) ? 1u : 0u);
-            tc_mma_tf32_ts(tmem_base, a_hi + aadv, b_lo + badv, idesc, 1u);
-            tc_mma_tf32_ts(tmem_base, a_hi + aadv, b_hi + badv, idesc, 1u);
+            tc_mma_tf32_ts(d, a_lo + aadv, b_hi + badv, idesc, first);
+            tc_mma_tf32_ts(d, a_hi + aadv, b_lo + badv, idesc, 1u);
+            tc_mma_tf32_ts(d, a_hi + aadv, b_hi + badv, idesc, 1u);
           } else {
-            tc_mma_tf32_ts(tmem_base, a_hi + aadv, b_hi + badv, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+            tc_mma_tf32_ts(d, a_hi + aadv, b_hi + badv, idesc, first);
           }
         }
         tc_commit(a_empty + 8 * sa);
@@ -1017,66 +754,37 @@ int spconv_forward_tc(const float *features, const float *weight, const float *p
                                residual, relu, out, st);
   }
   const int nsplit = precision == BEVB200_PREC_TF32X3 ? 2 : 1;
-  TcParams p;
-  p.features = features; p.nbr = nbr; p.scale = scale; p.shift = shift; p.residual = residual;
-  p.out = out; p.n_in = n_in; p.n_out = n_out; p.c_in = c_in; p.c_out = c_out; p.kvol = kvol;
-  p.relu = relu;
-  p.nkb = tc_nkb(c_in, kvol);
-  p.cin_shift = 0;
-  while ((1 << p.cin_shift) < c_in) ++p.cin_shift;
-  p.acc_cols = c_out < 32 ? 32 : c_out;
-  p.num_tiles = (n_out + kTileM - 1) / kTileM;
-  // shared-memory rings: 3 A stages (gathered rows, 16 KB per split part) + as many weight
-  // stages as fit (deep prefetch hides the L2 latency of the per-K-block weight fetch)
-  const int a_stage = nsplit * kABlockBytes, b_stage = nsplit * c_out * 128;
-  const int nbr_bytes = 2 * kvol * kTileM * 4;
-  p.nsa = 3;
-  int nsb = (225 * 1024 - nbr_bytes - p.nsa * a_stage) / b_stage;
-  if (nsb > kMaxStages) nsb = kMaxStages;
-  if (nsb < 2) nsb = 2;
-  p.nsb = nsb;
-  const size_t smem = (size_t)p.nsa * a_stage + (size_t)p.nsb * b_stage + nbr_bytes + 1024;
-  // kernel variant: v2 (tile per CTA, 2 CTAs/SM) or v3 (persistent).  BEVB200_SPCONV_TC_VARIANT
-  // = 2 / 3 forces one; the default picks per shape from measurements.
+  const int nkb = tc_nkb(c_in, kvol);
+  int cin_shift = 0;
+  while ((1 << cin_shift) < c_in) ++cin_shift;
+  const int acc_cols = c_out < 32 ? 32 : c_out;
+  const int nbr_bytes = kvol * kTileM * 4;
+  const int grid_tiles = (n_out + kTileM - 1) / kTileM;
+
+  // kernel variant: 4 (default: A in tensor memory) or 2 (both operands in shared memory; kept
+  // for A/B measurements).  BEVB200_SPCONV_TC_VARIANT=2 forces the latter.
   static int forced = -1;
   if (forced < 0) {
     const char *e = getenv("BEVB200_SPCONV_TC_VARIANT");
     forced = e ? atoi(e) : 0;
   }
-  int variant = forced ? forced : 4;
-  if (variant == 3 && p.nkb < 12) variant = 2;   // v3's cross-tile prefetch needs >= 12 K blocks per tile
-  TcParamsV2 p2;
-  p2.features = features; p2.nbr = nbr; p2.scale = scale; p2.shift = shift; p2.residual = residual;
-  p2.out = out; p2.n_in = n_in; p2.n_out = n_out; p2.c_in = c_in; p2.c_out = c_out; p2.kvol = kvol;
-  p2.relu = relu; p2.nkb = p.nkb; p2.cin_shift = p.cin_shift; p2.tmem_cols = p.acc_cols;
-  size_t smem2 = 0;
-  {
-    const int stage_bytes = nsplit * (kABlockBytes + c_out * 128);
-    const int nbr1 = kvol * kTileM * 4;
-    int ns = 2;
-    if (2 * stage_bytes + nbr1 + 1024 > 111 * 1024) {
-      ns = (215 * 1024 - nbr1) / stage_bytes;
-      if (ns > 4) ns = 4;
-    }
-    p2.nstages = ns;
-    smem2 = (size_t)ns * stage_bytes + nbr1 + 1024;
-  }
+  const int variant = forced == 2 ? 2 : 4;
+
   float *packed = nullptr;
+  const float *wpacked = packed_in;
   if (packed_in == nullptr) {
     BEVB200_CUDA(cudaMallocAsync((void **)&packed, spconv_packed_bytes(c_in, c_out, kvol, precision), st));
     int rc = spconv_pack_weights(weight, c_in, c_out, kvol, precision, packed, st);
     if (rc) return rc;
-    p.wpacked = packed;
-  } else {
-    p.wpacked = packed_in;
+    wpacked = packed;
   }
-  p2.wpacked = p.wpacked;
+
   if (variant == 4) {
     TcParamsV4 p4;
     p4.features = features; p4.nbr = nbr; p4.scale = scale; p4.shift = shift; p4.residual = residual;
     p4.out = out; p4.n_in = n_in; p4.n_out = n_out; p4.c_in = c_in; p4.c_out = c_out; p4.kvol = kvol;
-    p4.relu = relu; p4.nkb = p.nkb; p4.cin_shift = p.cin_shift; p4.wpacked = p.wpacked;
-    p4.acc_cols = p.acc_cols;
+    p4.relu = relu; p4.nkb = nkb; p4.cin_shift = cin_shift; p4.wpacked = wpacked;
+    p4.acc_cols = acc_cols;
     {
       // dev profiling: BEVB200_TC_PROF=<device pointer of 8 int64 counters, hex>
       static long long *prof_ptr = (long long *)-1;
@@ -1086,28 +794,36 @@ int spconv_forward_tc(const float *features, const float *weight, const float *p
       }
       p4.prof = prof_ptr;
     }
-    // 256 TMEM columns per CTA (two CTAs per SM): accumulator + A ring
-    p4.nsa = (256 - p4.acc_cols) / (nsplit * 32);
+    // 256 TMEM columns per CTA (two CTAs per SM): nacc accumulators + A ring (>= 2 stages)
+    static int forced_nacc = -1;
+    if (forced_nacc < 0) {
+      const char *e = getenv("BEVB200_SPCONV_NACC");
+      forced_nacc = e ? atoi(e) : 0;
+    }
+    int nacc = forced_nacc ? forced_nacc : (c_out <= 32 ? 4 : (c_out <= 64 ? 2 : 1));
+    while (nacc > 1 && nacc * p4.acc_cols + 2 * nsplit * 32 > 256) nacc >>= 1;
+    if (nacc != 1 && nacc != 2 && nacc != 4) nacc = 1;
+    p4.nacc = nacc;
+    p4.nsa = (256 - nacc * p4.acc_cols) / (nsplit * 32);
     if (p4.nsa > 4) p4.nsa = 4;
     p4.tmem_cols = 256;
-    const int b_stage4 = nsplit * c_out * 128, nbr4 = kvol * kTileM * 4;
-    int nsb4 = (110 * 1024 - nbr4 - 1024) / b_stage4;
+    const int b_stage4 = nsplit * c_out * 128;
+    int nsb4 = (110 * 1024 - nbr_bytes - 1024) / b_stage4;
     if (nsb4 > kMaxStages) nsb4 = kMaxStages;
     if (nsb4 < 2) nsb4 = 2;
     p4.nsb = nsb4;
-    const size_t smem4 = (size_t)nsb4 * b_stage4 + nbr4 + 1024;
-    // thread-block clusters: the weight stream is the dominant L2 traffic for wide layers
-    // (27*Cin*Cout*8 bytes per 128-row tile); a cluster of 2 halves it
+    const size_t smem4 = (size_t)nsb4 * b_stage4 + nbr_bytes + 1024;
+    // thread-block clusters multicast the weight stages (halves the L2 reads of the weights);
+    // measured: no gain on B200 for this kernel (the limit is per-SM ingest), so off by default
     static int forced_csz = -1;
     if (forced_csz < 0) {
       const char *e = getenv("BEVB200_SPCONV_CLUSTER");
       forced_csz = e ? atoi(e) : 0;
     }
-    int csz = forced_csz ? forced_csz : ((long long)c_in * c_out >= 64 * 64 ? 2 : 1);
+    int csz = forced_csz ? forced_csz : 1;
     if (csz != 1 && csz != 2 && csz != 4) csz = 1;
     p4.csz = csz;
-    int grid4 = (n_out + kTileM - 1) / kTileM;
-    grid4 = (grid4 + csz - 1) / csz * csz;
+    const int grid4 = (grid_tiles + csz - 1) / csz * csz;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid4);
@@ -1131,32 +847,28 @@ int spconv_forward_tc(const float *features, const float *weight, const float *p
       BEVB200_CUDA(cudaLaunchKernelEx(&cfg, spconv_tc_kernel_v4<1>, p4));
     }
     ++g_launch_count;
-    if (packed) BEVB200_CUDA(cudaFreeAsync(packed, st));
-    return BEVB200_OK;
-  }
-  if (variant == 2) {
-    const int grid2 = (n_out + kTileM - 1) / kTileM;
+  } else {
+    TcParamsV2 p2;
+    p2.features = features; p2.nbr = nbr; p2.scale = scale; p2.shift = shift; p2.residual = residual;
+    p2.out = out; p2.n_in = n_in; p2.n_out = n_out; p2.c_in = c_in; p2.c_out = c_out; p2.kvol = kvol;
+    p2.relu = relu; p2.nkb = nkb; p2.cin_shift = cin_shift; p2.tmem_cols = acc_cols; p2.wpacked = wpacked;
+    const int stage_bytes = nsplit * (kABlockBytes + c_out * 128);
+    int ns = 2;
+    if (2 * stage_bytes + nbr_bytes + 1024 > 111 * 1024) {
+      ns = (215 * 1024 - nbr_bytes) / stage_bytes;
+      if (ns > 4) ns = 4;
+    }
+    p2.nstages = ns;
+    const size_t smem2 = (size_t)ns * stage_bytes + nbr_bytes + 1024;
     if (nsplit == 2) {
       BEVB200_CUDA(cudaFuncSetAttribute(spconv_tc_kernel_v2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)smem2));
-      BEVB200_LAUNCH(spconv_tc_kernel_v2<2>, grid2, kTcThreads, smem2, st, p2);
+      BEVB200_LAUNCH(spconv_tc_kernel_v2<2>, grid_tiles, kTcThreads, smem2, st, p2);
     } else {
       BEVB200_CUDA(cudaFuncSetAttribute(spconv_tc_kernel_v2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)smem2));
-      BEVB200_LAUNCH(spconv_tc_kernel_v2<1>, grid2, kTcThreads, smem2, st, p2);
+      BEVB200_LAUNCH(spconv_tc_kernel_v2<1>, grid_tiles, kTcThreads, smem2, st, p2);
     }
-    if (packed) BEVB200_CUDA(cudaFreeAsync(packed, st));
-    return BEVB200_OK;
-  }
-  const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;   // persistent: one CTA per SM
-  if (nsplit == 2) {
-    BEVB200_CUDA(cudaFuncSetAttribute(spconv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem));
-    BEVB200_LAUNCH(spconv_tc_kernel<2>, grid, kTcThreadsV3, smem, st, p);
-  } else {
-    BEVB200_CUDA(cudaFuncSetAttribute(spconv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem));
-    BEVB200_LAUNCH(spconv_tc_kernel<1>, grid, kTcThreadsV3, smem, st, p);
   }
   if (packed) BEVB200_CUDA(cudaFreeAsync(packed, st));
   return BEVB200_OK;
