@@ -211,14 +211,14 @@ int bevb200_spconv_forward(const float *features, const float *weight, const int
   if (precision == BEVB200_PREC_FP32)
     return spconv_forward_simt(features, weight, nbr, n_in, n_out, c_in, c_out, kernel_volume,
                                scale, shift, residual, relu, out, st);
-  if (precision == BEVB200_PREC_TF32X3 || precision == BEVB200_PREC_TF32)
+  if (precision == BEVB200_PREC_TF32X3 || precision == BEVB200_PREC_TF32 || precision == BEVB200_PREC_BF16X3)
     return spconv_forward_tc(features, weight, nullptr, nbr, n_in, n_out, c_in, c_out, kernel_volume,
                              scale, shift, residual, relu, precision, out, st);
   BEVB200_REQUIRE(false, "unknown precision mode");
 }
 
 size_t bevb200_spconv_packed_weight_bytes(int c_in, int c_out, int kernel_volume, int precision) {
-  if (precision != BEVB200_PREC_TF32X3 && precision != BEVB200_PREC_TF32) return 0;
+  if (precision != BEVB200_PREC_TF32X3 && precision != BEVB200_PREC_TF32 && precision != BEVB200_PREC_BF16X3) return 0;
   return spconv_packed_bytes(c_in, c_out, kernel_volume, precision);
 }
 

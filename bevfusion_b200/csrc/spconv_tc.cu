@@ -409,6 +409,30 @@ __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16])
         "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// instruction descriptor for kind::f16 with bf16 operands: c=F32 (bit 4), a=b=BF16 (1 at bits 7, 10)
+__host__ __device__ inline uint32_t umma_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// fp32 -> bf16 (round to nearest even), bit pattern in the low 16 bits
+__device__ __forceinline__ uint32_t bf16_bits(float f) {
+  uint32_t u = __float_as_uint(f);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return u >> 16;
+}
 __device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
                                                uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -444,8 +468,14 @@ __global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v4(const TcPar
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
+  // NSPLIT: 1 = single-pass TF32, 2 = 3xTF32 (hi/lo tf32 parts), 3 = BF16x3 (a = bf16 hi + bf16 lo;
+  // hi*hi + hi*lo + lo*hi with kind::f16: half the MMAs and half the operand bytes of 3xTF32 at
+  // 2^-17 per-product error).  In BF16 mode one 128-byte weight row holds 64 K values, i.e. one
+  // weight stage serves TWO 32-wide K blocks of A.
+  constexpr bool BF = NSPLIT == 3;
+  constexpr int NPART = BF ? 2 : NSPLIT;
   const int b_part_bytes = p.c_out * 128;
-  const int b_stage_bytes = NSPLIT * b_part_bytes;
+  const int b_stage_bytes = NPART * b_part_bytes;
   __shared__ uint64_t bars[4 * kMaxStages + 1];
   __shared__ uint32_t tmem_base_s;
   const uint32_t a_full = smem_u32(&bars[0]), a_empty = smem_u32(&bars[kMaxStages]);
@@ -481,7 +511,7 @@ __global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v4(const TcPar
   const uint32_t tmem_base = tmem_base_s;
   const uint16_t cmask = (uint16_t)((1u << p.csz) - 1u);
   const uint32_t a_ring = tmem_base + (uint32_t)(p.nacc * p.acc_cols);   // column offset of A stage 0
-  constexpr uint32_t kAStageCols = NSPLIT * 32;
+  constexpr uint32_t kAStageCols = BF ? 32u : (uint32_t)NSPLIT * 32u;   // BF16: 16 cols hi | 16 cols lo
 
   if (warp < 8) {
     // =============================== producers ===========================================
@@ -541,6 +571,25 @@ __global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v4(const TcPar
           __syncwarp();
           tc_fence_after();
           const long long t1 = clock64();
+          if constexpr (BF) {
+            // 16 K values of this row -> 8 packed bf16 words hi + 8 words lo (k even in the low half)
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float f[4] = {v[jj][j].x, v[jj][j].y, v[jj][j].z, v[jj][j].w};
+              uint32_t h[4], l[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                h[e] = bf16_bits(f[e]);
+                l[e] = bf16_bits(f[e] - __uint_as_float(h[e] << 16));
+              }
+              hi[2 * j] = h[0] | (h[1] << 16); hi[2 * j + 1] = h[2] | (h[3] << 16);
+              lo[2 * j] = l[0] | (l[1] << 16); lo[2 * j + 1] = l[2] | (l[3] << 16);
+            }
+            const uint32_t col = a_ring + (uint32_t)s * kAStageCols + (uint32_t)(half * 8);
+            tc_st8(lane_base + col, hi);
+            tc_st8(lane_base + col + 16u, lo);
+          } else {
           uint32_t hi[16], lo[16];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -554,6 +603,7 @@ __global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v4(const TcPar
           const uint32_t col = a_ring + (uint32_t)s * kAStageCols + (uint32_t)(half * 16);
           tc_st16(lane_base + col, hi);
           if (NSPLIT == 2) tc_st16(lane_base + col + 32u, lo);
+          }
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
           tc_fence_before();
           __syncwarp();
@@ -615,33 +665,40 @@ __global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v4(const TcPar
     }
   } else if (warp == 8) {
     // =============================== MMA issuer ==========================================
-    const uint32_t idesc = umma_idesc_tf32(kTileM, p.c_out);
+    const uint32_t idesc = BF ? umma_idesc_bf16(kTileM, p.c_out) : umma_idesc_tf32(kTileM, p.c_out);
     for (int it = 0; it < n_iters; ++it) {
-      const int sa = it % p.nsa, sb = it % p.nsb;
+      const int gb = BF ? (it >> 1) : it;          // weight stage index (64 K values per stage in BF16)
+      const int sa = it % p.nsa, sb = gb % p.nsb;
       const long long m0 = clock64();
       mbar_wait(a_full + 8 * sa, (uint32_t)(it / p.nsa) & 1u);
       const long long m1 = clock64();
-      mbar_wait(b_full + 8 * sb, (uint32_t)(it / p.nsb) & 1u);
+      mbar_wait(b_full + 8 * sb, (uint32_t)(gb / p.nsb) & 1u);
       tc_fence_after();
       const long long m2 = clock64();
       if (p.prof && blockIdx.x == 0 && lane == 0) { p.prof[4] += m1 - m0; p.prof[5] += m2 - m1; }
       if (elect_one_sync()) {
         const uint32_t a_hi = a_ring + (uint32_t)sa * kAStageCols;   // lane 0, column offset
-        const uint32_t a_lo = a_hi + 32u;
+        const uint32_t a_lo = a_hi + (BF ? 16u : 32u);
         const uint32_t bstage = smem_base + (uint32_t)sb * (uint32_t)b_stage_bytes;
         const uint64_t b_hi = umma_desc_sw128(bstage);
         const uint64_t b_lo = umma_desc_sw128(bstage + b_part_bytes);
+        constexpr int KSTEPS = BF ? 2 : 4;           // 16 bf16 / 8 tf32 per MMA = 32 B of K either way
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          const uint64_t badv = (uint64_t)(ks * 2);   // +32 B along K inside the swizzled row
-          const uint32_t aadv = (uint32_t)(ks * 8);   // +8 tf32 = 8 TMEM columns
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+          // +32 B along K inside the 128-byte swizzled weight row (BF16: odd K blocks use its 2nd half)
+          const uint64_t badv = (uint64_t)(ks * 2 + (BF ? (it & 1) * 4 : 0));
+          const uint32_t aadv = (uint32_t)(ks * 8);   // 8 TMEM columns per K step (8 tf32 / 16 bf16)
           // consecutive MMAs into ONE accumulator serialise at ~64 clk each whatever N is
           // (measured: 12 MMAs = ~780 clk for N = 16 .. 64); K step ks therefore accumulates into
           // accumulator ks % nacc, the chains overlap in the tensor pipe, the epilogue adds them
           const int ai = ks & (p.nacc - 1);
           const uint32_t d = tmem_base + (uint32_t)(ai * p.acc_cols);
           const uint32_t first = (it == 0 && ks < p.nacc) ? 0u : 1u;
-          if (NSPLIT == 2) {
+          if constexpr (BF) {
+            tc_mma_bf16_ts(d, a_lo + aadv, b_hi + badv, idesc, first);
+            tc_mma_bf16_ts(d, a_hi + aadv, b_lo + badv, idesc, 1u);
+            tc_mma_bf16_ts(d, a_hi + aadv, b_hi + badv, idesc, 1u);
+          } else if (NSPLIT == 2) {
             tc_mma_tf32_ts(d, a_lo + aadv, b_hi + badv, idesc, first);
             tc_mma_tf32_ts(d, a_hi + aadv, b_lo + badv, idesc, 1u);
             tc_mma_tf32_ts(d, a_hi + aadv, b_hi + badv, idesc, 1u);
@@ -650,7 +707,9 @@ __global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v4(const TcPar
           }
         }
         tc_commit(a_empty + 8 * sa);
-        if (p.csz > 1) tc_commit_mcast(b_empty + 8 * sb, cmask); else tc_commit(b_empty + 8 * sb);
+        if (!BF || (it & 1) || it == n_iters - 1) {   // the weight stage is free after its last K block
+          if (p.csz > 1) tc_commit_mcast(b_empty + 8 * sb, cmask); else tc_commit(b_empty + 8 * sb);
+        }
         if (it == n_iters - 1) tc_commit(accbar);
         if (p.prof && blockIdx.x == 0) p.prof[6] += clock64() - m2;   // MMA issue + commits
       }
@@ -664,7 +723,8 @@ __global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v4(const TcPar
     if (lane == 0) {
       const uint32_t crank = p.csz > 1 ? cluster_ctarank() : 0u;
       const uint32_t slice = (uint32_t)b_stage_bytes / (uint32_t)p.csz;
-      for (int it = 0; it < n_iters; ++it) {
+      const int n_bstages = BF ? (n_iters + 1) / 2 : n_iters;
+      for (int it = 0; it < n_bstages; ++it) {
         const int sb = it % p.nsb;
         mbar_wait(b_empty + 8 * sb, ((uint32_t)(it / p.nsb) & 1u) ^ 1u);
         mbar_arrive_expect_tx(b_full + 8 * sb, (uint32_t)b_stage_bytes);
@@ -715,6 +775,31 @@ int spconv_forward_simt(const float *features, const float *weight, const int32_
                         const float *shift, const float *residual, int relu, float *out,
                         cudaStream_t st);
 
+// BF16x3 weights: packed [nb64][hi | lo][Cout][64 bf16] in the swizzled smem image; K index
+// kk = kb64*64 + c (c in 0..63), 16-byte chunk (c / 8) XOR (n & 7), element (c % 8) inside the chunk.
+__global__ void spconv_pack_weights_bf16_kernel(const float *__restrict__ w, int kvol, int c_in, int c_out,
+                                                int nb64, uint16_t *__restrict__ packed) {
+  const long long total = (long long)nb64 * c_out * 64;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(t % 64);
+    const int n = (int)((t / 64) % c_out);
+    const int kb = (int)(t / (64ll * c_out));
+    const int kk = kb * 64 + c;
+    const int k = kk / c_in, ci = kk % c_in;
+    const float v = k < kvol ? w[((long long)k * c_in + ci) * c_out + n] : 0.f;
+    uint32_t u = __float_as_uint(v);
+    u += 0x7fffu + ((u >> 16) & 1u);
+    const uint32_t hb = u >> 16;
+    const float lo = v - __uint_as_float(hb << 16);
+    uint32_t ul = __float_as_uint(lo);
+    ul += 0x7fffu + ((ul >> 16) & 1u);
+    const int pos = n * 64 + ((((c >> 3) ^ (n & 7)) << 3) | (c & 7));
+    packed[((long long)kb * 2 + 0) * c_out * 64 + pos] = (uint16_t)hb;
+    packed[((long long)kb * 2 + 1) * c_out * 64 + pos] = (uint16_t)(ul >> 16);
+  }
+}
+
 static bool tc_shape_ok(int c_in, int c_out, int kvol) {
   return (c_out == 16 || c_out == 32 || c_out == 64 || c_out == 128) &&
          (c_in == 16 || c_in == 32 || c_in == 64 || c_in == 128) && kvol >= 1 && kvol <= 27;
@@ -724,12 +809,20 @@ static int tc_nkb(int c_in, int kvol) { return (kvol * c_in + kKBlock - 1) / kKB
 
 size_t spconv_packed_bytes(int c_in, int c_out, int kvol, int precision) {
   if (!tc_shape_ok(c_in, c_out, kvol)) return 0;
+  if (precision == BEVB200_PREC_BF16X3)
+    return (size_t)((tc_nkb(c_in, kvol) + 1) / 2) * 2 * c_out * 64 * sizeof(uint16_t);
   const int nsplit = precision == BEVB200_PREC_TF32X3 ? 2 : 1;
   return (size_t)tc_nkb(c_in, kvol) * nsplit * c_out * 32 * sizeof(float);
 }
 
 int spconv_pack_weights(const float *weight, int c_in, int c_out, int kvol, int precision,
                         float *packed, cudaStream_t st) {
+  if (precision == BEVB200_PREC_BF16X3) {
+    const int nb64 = (tc_nkb(c_in, kvol) + 1) / 2;
+    BEVB200_LAUNCH(spconv_pack_weights_bf16_kernel, grid_for((long long)nb64 * c_out * 64, 256), 256, 0, st,
+                   weight, kvol, c_in, c_out, nb64, (uint16_t *)packed);
+    return BEVB200_OK;
+  }
   const int nsplit = precision == BEVB200_PREC_TF32X3 ? 2 : 1;
   const int nkb = tc_nkb(c_in, kvol);
   BEVB200_LAUNCH(spconv_pack_weights_kernel, grid_for((long long)nkb * c_out * 32, 256), 256, 0, st,
@@ -753,7 +846,8 @@ int spconv_forward_tc(const float *features, const float *weight, const float *p
     return spconv_forward_simt(features, weight, nbr, n_in, n_out, c_in, c_out, kvol, scale, shift,
                                residual, relu, out, st);
   }
-  const int nsplit = precision == BEVB200_PREC_TF32X3 ? 2 : 1;
+  const bool bf = precision == BEVB200_PREC_BF16X3;
+  const int nsplit = precision == BEVB200_PREC_TF32X3 ? 2 : 1;   // tf32 parts (unused in BF16 mode)
   const int nkb = tc_nkb(c_in, kvol);
   int cin_shift = 0;
   while ((1 << cin_shift) < c_in) ++cin_shift;
@@ -768,7 +862,7 @@ int spconv_forward_tc(const float *features, const float *weight, const float *p
     const char *e = getenv("BEVB200_SPCONV_TC_VARIANT");
     forced = e ? atoi(e) : 0;
   }
-  const int variant = forced == 2 ? 2 : 4;
+  const int variant = (forced == 2 && !bf) ? 2 : 4;
 
   float *packed = nullptr;
   const float *wpacked = packed_in;
@@ -801,13 +895,15 @@ int spconv_forward_tc(const float *features, const float *weight, const float *p
       forced_nacc = e ? atoi(e) : 0;
     }
     int nacc = forced_nacc ? forced_nacc : (c_out <= 32 ? 4 : (c_out <= 64 ? 2 : 1));
-    while (nacc > 1 && nacc * p4.acc_cols + 2 * nsplit * 32 > 256) nacc >>= 1;
+    const int a_stage_cols = bf ? 32 : nsplit * 32;
+    if (bf && nacc > 2) nacc = 2;                 // BF16 mode has 2 K steps per K block
+    while (nacc > 1 && nacc * p4.acc_cols + 2 * a_stage_cols > 256) nacc >>= 1;
     if (nacc != 1 && nacc != 2 && nacc != 4) nacc = 1;
     p4.nacc = nacc;
-    p4.nsa = (256 - nacc * p4.acc_cols) / (nsplit * 32);
+    p4.nsa = (256 - nacc * p4.acc_cols) / a_stage_cols;
     if (p4.nsa > 4) p4.nsa = 4;
     p4.tmem_cols = 256;
-    const int b_stage4 = nsplit * c_out * 128;
+    const int b_stage4 = (bf ? 2 : nsplit) * c_out * 128;
     int nsb4 = (110 * 1024 - nbr_bytes - 1024) / b_stage4;
     if (nsb4 > kMaxStages) nsb4 = kMaxStages;
     if (nsb4 < 2) nsb4 = 2;
@@ -837,7 +933,11 @@ int spconv_forward_tc(const float *features, const float *weight, const float *p
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (nsplit == 2) {
+    if (bf) {
+      BEVB200_CUDA(cudaFuncSetAttribute(spconv_tc_kernel_v4<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem4));
+      BEVB200_CUDA(cudaLaunchKernelEx(&cfg, spconv_tc_kernel_v4<3>, p4));
+    } else if (nsplit == 2) {
       BEVB200_CUDA(cudaFuncSetAttribute(spconv_tc_kernel_v4<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)smem4));
       BEVB200_CUDA(cudaLaunchKernelEx(&cfg, spconv_tc_kernel_v4<2>, p4));

@@ -17,8 +17,8 @@ import torch
 
 from .. import _C
 
-PREC_FP32, PREC_TF32X3, PREC_TF32 = 0, 1, 2
-_PREC_NAMES = {"fp32": PREC_FP32, "tf32x3": PREC_TF32X3, "tf32": PREC_TF32}
+PREC_FP32, PREC_TF32X3, PREC_TF32, PREC_BF16X3 = 0, 1, 2, 3
+_PREC_NAMES = {"fp32": PREC_FP32, "tf32x3": PREC_TF32X3, "tf32": PREC_TF32, "bf16x3": PREC_BF16X3}
 
 
 def default_precision():

@@ -249,10 +249,13 @@ BEVB200_API int bevb200_pairs_to_nbr(const int32_t *indice_pairs, const int32_t 
  * precision: BEVB200_PREC_FP32  exact fp32 FFMA accumulation (SIMT)
  *            BEVB200_PREC_TF32X3 tcgen05 tensor cores, 3xTF32 split (fp32-class accuracy)
  *            BEVB200_PREC_TF32   tcgen05 single-pass TF32 (fast mode, ~1e-3 rel)
+ *            BEVB200_PREC_BF16X3 tcgen05 bf16 hi/lo split: half the MMAs and operand bytes of TF32X3,
+ *                                per-product error ~2^-17 (measured ~1e-5 relative per layer)
  */
 #define BEVB200_PREC_FP32 0
 #define BEVB200_PREC_TF32X3 1
 #define BEVB200_PREC_TF32 2
+#define BEVB200_PREC_BF16X3 3 /* tcgen05 kind::f16: a = bf16 hi + bf16 lo, hi*hi + hi*lo + lo*hi (3 MMAs per 16 K) */
 BEVB200_API int bevb200_spconv_forward(const float *features, const float *weight, const int32_t *nbr,
                            int n_in, int n_out, int c_in, int c_out, int kernel_volume,
                            const float *scale, const float *shift, const float *residual,

@@ -23,7 +23,7 @@ for (cin, cout) in [(32, 32), (16, 16), (64, 64), (128, 128), (16, 32), (64, 128
     gold, gids, _ = oracle.sparse_conv(feat, idx, B, shape, W, [3]*3, [1]*3, [1]*3, [1]*3, True, acc64=True)
     rb, _ = ops.get_rulebook(torch.from_numpy(idx).to(dev), B, shape, 3, 1, 1, 1, 0, True)
     f, w = torch.from_numpy(feat).to(dev), torch.from_numpy(W).to(dev)
-    for prec in (0, 1, 2):
+    for prec in (0, 1, 2, 3):
         out = ops.sparse_conv(f, w, rb.nbr, rb.n_out, precision=prec)
         torch.cuda.synchronize()
         err = np.abs(out.cpu().numpy() - gold).max() / np.abs(gold).max()
