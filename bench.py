@@ -67,7 +67,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -209,7 +209,8 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     # --- device-resident throughput ------------------------------------------------------
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if rank == 0:          # one nvidia-smi poller per job (its driver queries can stall CUDA calls)
+        sampler.start()
     timers = {}
     _C.reset_launch_count()
     barrier()

@@ -40,6 +40,7 @@ _SIGNATURES = {
     "bevb200_rulebook_prepare": (c_int, [_P, c_int, c_int] + [_P] * 6 + [c_int, _P, _P, c_size_t, _P]),
     "bevb200_rulebook_fill": (c_int, [_P, c_int, c_int] + [_P] * 6 + [c_int, c_int, _P, _P, _P,
                                                                        c_size_t, _P]),
+    "bevb200_rulebook_fill_subm_sorted": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
     "bevb200_rulebook_to_pairs": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P]),
     "bevb200_pairs_to_nbr": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P]),
     "bevb200_spconv_forward": (c_int, [_P, _P, _P] + [c_int] * 5 + [_P, _P, _P, c_int, c_int, _P, _P]),

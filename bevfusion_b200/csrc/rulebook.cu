@@ -79,7 +79,7 @@ __global__ void rb_subm_nbr_kernel(const int32_t *__restrict__ indices, int n, C
     if ((unsigned)c.x < (unsigned)g.batch && (unsigned)x < (unsigned)g.out_shape[0] &&
         (unsigned)y < (unsigned)g.out_shape[1] && (unsigned)z < (unsigned)g.out_shape[2]) {
       int r = site_rank(bits, prefix, flat_site(c.x, x, y, z, g.out_shape));
-      if (r >= 0) row = rank2row[r];
+      if (r >= 0) row = rank2row ? rank2row[r] : r;
     }
     nbr[t] = row;
   }
@@ -335,6 +335,29 @@ int bevb200_rulebook_fill(const int32_t *indices, int n_in, int batch_size,
     BEVB200_LAUNCH(rb_conv_sites_kernel<true>, grid_for(n_in, 128), 128, 0, st, indices, n_in, g, w.bits,
                    (const uint32_t *)w.prefix, n_out, nbr);
   }
+  return BEVB200_OK;
+}
+
+int bevb200_rulebook_fill_subm_sorted(const int32_t *indices, int n, int batch_size,
+                                      const int32_t *spatial_shape_host, const int32_t *ksize_host,
+                                      const int32_t *dilation_host, int32_t *nbr, void *workspace,
+                                      size_t workspace_bytes, void *stream) {
+  BEVB200_REQUIRE(n >= 0 && batch_size > 0, "bad sizes");
+  BEVB200_REQUIRE(spatial_shape_host && ksize_host && dilation_host, "null argument");
+  ConvGeom g;
+  const int32_t ones[3] = {1, 1, 1}, zeros[3] = {0, 0, 0};
+  BEVB200_REQUIRE(make_geom(batch_size, spatial_shape_host, spatial_shape_host, ksize_host, ones, zeros,
+                            dilation_host, 1, &g) == 0, "bad convolution geometry");
+  RbWs w;
+  size_t need = rb_layout(0, batch_size, spatial_shape_host, workspace, workspace_bytes, &w);
+  if (workspace == nullptr || workspace_bytes < need) {
+    snprintf(g_last_error, sizeof(g_last_error), "rulebook: workspace too small (%zu < %zu)", workspace_bytes, need);
+    return BEVB200_EWORKSPACE;
+  }
+  if (n == 0) return BEVB200_OK;
+  BEVB200_REQUIRE(indices && nbr, "null argument");
+  BEVB200_LAUNCH(rb_subm_nbr_kernel, grid_for((long long)n * g.kvol, 256), 256, 0, (cudaStream_t)stream,
+                 indices, n, g, w.bits, w.prefix, (const int32_t *)nullptr, nbr);
   return BEVB200_OK;
 }
 

@@ -59,10 +59,13 @@ def _vp(arr):
 class Rulebook:
     """Neighbour-table rulebook of one sparse conv: nbr[k, o] = input row or -1."""
 
-    def __init__(self, outids, nbr, n_in, n_out, kernel_volume):
+    def __init__(self, outids, nbr, n_in, n_out, kernel_volume, site_state=None):
         self.outids, self.nbr = outids, nbr
         self.n_in, self.n_out, self.kernel_volume = n_in, n_out, kernel_volume
         self._pairs = None
+        # strided convs keep (workspace, batch, out_shape): the site bitmap + ranks of their OUTPUT
+        # grid are exactly what a SubM rulebook over those outputs needs
+        self.site_state = site_state
 
     def pairs(self):
         """(indice_pairs [K, 2, n_in] int32 (-1 padded), indice_pair_num [K] int32): the
@@ -82,6 +85,9 @@ class Rulebook:
 
 def _listify(v, ndim):
     return list(v) if isinstance(v, (list, tuple)) else [v] * ndim
+
+
+_SITE_STATE = {}   # outids.data_ptr() -> (outids tensor, workspace, batch, out_shape) of strided convs
 
 
 def get_rulebook(indices, batch_size, spatial_shape, ksize=3, stride=1, padding=0, dilation=1,
@@ -110,6 +116,18 @@ def get_rulebook(indices, batch_size, spatial_shape, ksize=3, stride=1, padding=
     L = _C.lib()
     hs, ho, hk, hst, hp, hd = (_i32(spatial_shape), _i32(out_shape), _i32(ksize), _i32(stride),
                                _i32(padding), _i32(dilation))
+    if subm:
+        st = _SITE_STATE.get(indices.data_ptr())
+        if (st is not None and st[0] is indices and st[2] == batch_size and st[3] == spatial_shape
+                and n_in > 0):
+            # rows are the outputs of a strided conv built moments ago: reuse its bitmap + ranks
+            with torch.cuda.device(dev):
+                nbr = torch.empty((kvol, n_in), dtype=torch.int32, device=dev)
+                rc = L.bevb200_rulebook_fill_subm_sorted(_C.ptr(indices), n_in, batch_size, _vp(hs), _vp(hk),
+                                                         _vp(hd), _C.ptr(nbr), _C.ptr(st[1]), st[1].numel(),
+                                                         _C.current_stream(dev))
+            _C.check(rc, "rulebook_fill_subm_sorted")
+            return Rulebook(indices, nbr, n_in, n_in, kvol), out_shape
     with torch.cuda.device(dev):
         stream = _C.current_stream(dev)
         ws = torch.empty(max(L.bevb200_rulebook_workspace_bytes(n_in, batch_size, _vp(ho)), 256),
@@ -129,7 +147,14 @@ def get_rulebook(indices, batch_size, spatial_shape, ksize=3, stride=1, padding=
                                      _vp(hst), _vp(hp), _vp(hd), int(bool(subm)), n_out,
                                      _C.ptr(outids), _C.ptr(nbr), _C.ptr(ws), ws.numel(), stream)
         _C.check(rc, "rulebook_fill")
-    return Rulebook(outids, nbr, n_in, n_out, kvol), out_shape
+    rb = Rulebook(outids, nbr, n_in, n_out, kvol)
+    if not subm and n_out > 0:
+        # remember the output-site state while `outids` is alive (one entry per strided conv; the
+        # dict is pruned when it grows -- entries are only valid for the identical tensor object)
+        if len(_SITE_STATE) > 16:
+            _SITE_STATE.clear()
+        _SITE_STATE[outids.data_ptr()] = (outids, ws, batch_size, list(out_shape))
+    return rb, out_shape
 
 
 def get_indice_pairs(indices, batch_size, spatial_shape, ksize=3, stride=1, padding=0, dilation=1,

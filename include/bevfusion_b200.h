@@ -225,6 +225,15 @@ BEVB200_API int bevb200_rulebook_fill(const int32_t *indices, int n_in, int batc
                           int subm, int n_out, int32_t *out_indices, int32_t *nbr,
                           void *workspace, size_t workspace_bytes, void *stream);
 
+/* SubM rulebook of a tensor whose rows ARE the outputs of the strided conv whose
+ * bevb200_rulebook_prepare() left its state in `workspace` (same batch size and output grid =
+ * this tensor's spatial shape): the site bitmap and its ranks are reused as they are (the rows
+ * are already in rank order), so no marking / scan / rank table pass is needed. */
+BEVB200_API int bevb200_rulebook_fill_subm_sorted(const int32_t *indices, int n, int batch_size,
+                                      const int32_t *spatial_shape_host, const int32_t *ksize_host,
+                                      const int32_t *dilation_host, int32_t *nbr, void *workspace,
+                                      size_t workspace_bytes, void *stream);
+
 /* nbr[K, n_out] -> indicePairs[K, 2, n_in] (-1 padded) + indiceNum[K]
  * (layout of spconv_ops.h:53-57).  Pairs of one offset are emitted in ascending output
  * row (the reference's GPU order is atomic-arrival order, i.e. unspecified). */
