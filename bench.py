@@ -349,7 +349,8 @@ def run_ours(args, rank, world, local_rank):
                          "MMAs whose dense peak is half the bf16 peak used here; traffic = sum over the 20 "
                          "tensor-core convs of the ncu capture")
     dominant = roof_enc if stages["encoder_ms"] >= stages["bev_pool_ms"] else roof_pool
-    cpu = None if args.no_cpu_baseline else cpu_baseline(n_steps=1)
+    # the CPU baseline is timed on rank 0 at N = 1 only
+    cpu = None if (args.no_cpu_baseline or world > 1) else cpu_baseline(n_steps=1)
     line = {
         "metric": METRIC, "value": round(world * 1000.0 / ms_per_step, 3), "unit": "frames/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

@@ -552,7 +552,7 @@ __global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v4(const TcPar
                         : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
-    constexpr int PD = 4;
+    constexpr int PD = 3;   // K blocks prefetched in registers (4 spills under the 2-CTA/SM register cap)
     float4 v[PD][4];
 #pragma unroll
     for (int j = 0; j < PD; ++j)
