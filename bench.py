@@ -348,6 +348,15 @@ def run_ours(args, rank, world, local_rank):
                     note="useful FLOPs = sum 2*pairs*Cin*Cout; issued tensor work is 3x (3xTF32 split) on TF32 "
                          "MMAs whose dense peak is half the bf16 peak used here; traffic = sum over the 20 "
                          "tensor-core convs of the ncu capture")
+    # hard_voxelize + mean: algorithmic bytes 4*F*N (points) + M*(4*P*F + 16) (voxels, coors, num) -- latency bound
+    n_pts, m_vox = int(pts.shape[0]), int(v.shape[0])
+    vox_bytes = 4 * 5 * n_pts + m_vox * (4 * 10 * 5 + 16)
+    vox_gbs = vox_bytes / (stages["voxelize_ms"] * 1e-3) / 1e9
+    roof_vox = dict(kernel="hard_voxelize (5 kernels + scan) + voxel_mean", bound="hbm", achieved=round(vox_gbs, 1),
+                    peak=peaks["hbm_gbs"], unit="GB/s", frac=round(vox_gbs / peaks["hbm_gbs"], 4), traffic=None,
+                    ms=round(stages["voxelize_ms"], 4), algorithmic_bytes=vox_bytes,
+                    points_per_s=round(n_pts / (stages["voxelize_ms"] * 1e-3)), peak_source=peaks["source"],
+                    note="latency bound: 40 MB of algorithmic traffic in ~10 dependent launches")
     dominant = roof_enc if stages["encoder_ms"] >= stages["bev_pool_ms"] else roof_pool
     # the CPU baseline is timed on rank 0 at N = 1 only
     cpu = None if (args.no_cpu_baseline or world > 1) else cpu_baseline(n_steps=1)
@@ -371,7 +380,7 @@ def run_ours(args, rank, world, local_rank):
                            "note": "backward = bevpool_bwd_kernel through perm (660 MB algorithmic); fused lift+pool reads "
                                    "depth (8 MB) + L2-resident ctx (5.4 MB) instead of the 638 MB lifted volume"},
         "roofline": dominant, "roofline_bev_pool": roof_pool, "roofline_bev_pool_op": roof_pool_op,
-        "roofline_encoder": roof_enc,
+        "roofline_encoder": roof_enc, "roofline_voxelize": roof_vox,
         "cpu_baseline": cpu, "clocks": clocks,
     }
     print(json.dumps(line))

@@ -150,3 +150,31 @@ def voxelize_mean(voxels, coors, num_points, batch_idx=0):
                                          _C.current_stream(voxels.device))
     _C.check(rc, "voxel_mean")
     return feats, coords4
+
+
+@torch.no_grad()
+def voxelize_batch(points, voxelize_module, voxelize_reduce=True):
+    """BEVFusion.voxelize (mmdet3d/models/fusion_models/bevfusion.py:169-197): per-sample hard
+    voxelization, batch index prepended to the coords (F.pad(c, (1, 0), value=k)), concatenation,
+    and -- with voxelize_reduce -- the mean over the points of each voxel.
+
+    points: list of [N_k, F] CUDA tensors.  Returns (feats, coords [M, 4] int32 (b, x, y, z), sizes)."""
+    feats, coords, sizes = [], [], []
+    for k, res in enumerate(points):
+        ret = voxelize_module(res)
+        if len(ret) == 3:
+            f, c, n = ret
+            if voxelize_reduce:
+                f, c4 = voxelize_mean(f.contiguous(), c.contiguous(), n.contiguous(), k)
+            else:
+                c4 = torch.nn.functional.pad(c, (1, 0), mode="constant", value=k)
+            sizes.append(n)
+        else:                      # dynamic voxelization: coords only
+            f, c = res, ret
+            c4 = torch.nn.functional.pad(c, (1, 0), mode="constant", value=k)
+        feats.append(f)
+        coords.append(c4)
+    feats = torch.cat(feats, dim=0)
+    coords = torch.cat(coords, dim=0)
+    sizes = torch.cat(sizes, dim=0) if sizes else sizes
+    return feats, coords, sizes

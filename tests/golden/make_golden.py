@@ -117,7 +117,69 @@ def gen_bev_pool():
                         pooled_geom=geom.numpy())
 
 
+def load_reference_base_transform(captured):
+    """exec mmdet3d/models/vtransforms/base.py from the reference tree with stubs for the two
+    imports it cannot satisfy here: mmcv.runner.force_fp32 (identity decorator) and
+    mmdet3d.ops.bev_pool (records its arguments and returns zeros of the op's output shape)."""
+    mmcv = types.ModuleType("mmcv"); runner = types.ModuleType("mmcv.runner")
+    runner.force_fp32 = lambda *a, **k: (lambda f: f)
+    mmcv.runner = runner
+    mm = types.ModuleType("mmdet3d"); ops = types.ModuleType("mmdet3d.ops")
+
+    def bev_pool_stub(x, geom_feats, B, D, H, W):
+        captured["x_rows"] = x.shape[0]
+        captured["coords"] = geom_feats.clone()
+        captured["dims"] = (int(B), int(D), int(H), int(W))
+        return torch.zeros(int(B), x.shape[1], int(D), int(H), int(W))
+    ops.bev_pool = bev_pool_stub
+    mm.ops = ops
+    saved = {k: sys.modules.get(k) for k in ("mmcv", "mmcv.runner", "mmdet3d", "mmdet3d.ops")}
+    sys.modules.update({"mmcv": mmcv, "mmcv.runner": runner, "mmdet3d": mm, "mmdet3d.ops": ops})
+    try:
+        src = open(os.path.join(REF, "mmdet3d/models/vtransforms/base.py")).read()
+        mod = types.ModuleType("_ref_vtransform_base")
+        exec(compile(src, "reference:vtransforms/base.py", "exec"), mod.__dict__)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return mod
+
+
+def gen_vtransform():
+    """get_geometry (base.py:92-135) and the index glue of BaseTransform.bev_pool (:141-169) run
+    from the REFERENCE source on the CPU for a 2-camera rig with image / lidar augmentation."""
+    from bevfusion_b200 import synthetic as S
+    captured = {}
+    mod = load_reference_base_transform(captured)
+    cfg = S.CONFIGS["tiny"]
+    t = mod.BaseTransform(in_channels=8, out_channels=cfg["C"], image_size=cfg["image_size"],
+                          feature_size=cfg["feature_size"], xbound=cfg["xbound"], ybound=cfg["ybound"],
+                          zbound=cfg["zbound"], dbound=cfg["dbound"])
+    B = 2
+    rig = S.camera_rig(cfg["n_cam"], cfg["image_size"], batch=B)
+    g = torch.Generator().manual_seed(4)
+    # a lidar augmentation (rotation about z + translation), different per sample
+    ang = torch.tensor([0.1, -0.25])
+    extra_rots = torch.stack([torch.tensor([[torch.cos(a), -torch.sin(a), 0.0], [torch.sin(a), torch.cos(a), 0.0],
+                                            [0.0, 0.0, 1.0]]) for a in ang])
+    extra_trans = torch.tensor([[0.5, -0.25, 0.1], [-1.0, 0.75, 0.0]])
+    geom = t.get_geometry(rig["camera2lidar_rots"], rig["camera2lidar_trans"], rig["intrins"], rig["post_rots"],
+                          rig["post_trans"], extra_rots=extra_rots, extra_trans=extra_trans)
+    D, fH, fW = geom.shape[2:5]
+    x = torch.randn(B, cfg["n_cam"], D, fH, fW, cfg["C"], generator=g)
+    t.bev_pool(geom, x)                         # records the op's inputs
+    np.savez_compressed(os.path.join(HERE, "vtransform_tiny.npz"), frustum=t.frustum.detach().numpy(),
+                        dx=t.dx.detach().numpy(), bx=t.bx.detach().numpy(), nx=t.nx.detach().numpy(),
+                        extra_rots=extra_rots.numpy(), extra_trans=extra_trans.numpy(),
+                        geom=geom.detach().numpy(), coords=captured["coords"].numpy(),
+                        dims=np.array(captured["dims"]), x_rows=captured["x_rows"])
+
+
 if __name__ == "__main__":
+    gen_vtransform()
     gen_voxelize()
     gen_spconv()
     gen_bev_pool()

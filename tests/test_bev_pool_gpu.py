@@ -273,3 +273,22 @@ def test_stress_c5_properties(cuda):
     out = plan.pool(x)
     kept_sum = x[perm[:t.n_kept]].double().sum()
     assert abs(float(out.double().sum() - kept_sum)) <= 1e-6 * float(x[perm[:t.n_kept]].double().abs().sum())
+
+
+def test_prepare_vs_reference_vtransform_fixture(cuda, golden_dir):
+    """device precompute (quantise / filter / rank / sort) vs the coords the REFERENCE's
+    BaseTransform.bev_pool produced for the same geometry (fixture from the reference source)."""
+    from bevfusion_b200.bev_pool import gen_dx_bx, prepare_from_geometry
+    from bevfusion_b200 import synthetic as S
+    g = np.load(os.path.join(golden_dir, "vtransform_tiny.npz"))
+    cfg = S.CONFIGS["tiny"]
+    dx, bx, nx = gen_dx_bx(cfg["xbound"], cfg["ybound"], cfg["zbound"])
+    t = prepare_from_geometry(torch.from_numpy(g["geom"]).to(cuda), dx, bx, nx, 2)
+    B, D, H, W = (int(v) for v in g["dims"])
+    ref_coords = g["coords"]                                       # kept rows, original order
+    assert t.n_kept == ref_coords.shape[0]
+    ranks = oracle.ranks_of(ref_coords, B, D, H, W)
+    order, rs, starts, lengths = oracle.sort_and_intervals(ranks)
+    assert np.array_equal(t.ranks[:t.n_kept].cpu().numpy(), rs.astype(np.int32))
+    assert np.array_equal(t.geom.cpu().numpy(), ref_coords[order].astype(np.int32))
+    assert np.array_equal(t.starts.cpu().numpy(), starts) and np.array_equal(t.lengths.cpu().numpy(), lengths)

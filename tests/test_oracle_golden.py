@@ -104,3 +104,30 @@ def test_hard_voxelize_edge_cases():
                    np.float32)
     v, c, n, m = oracle.hard_voxelize(pts, vs, cr, 3, 2)
     assert m == 2 and list(n) == [2, 1] and c.tolist() == [[0, 0, 0], [1, 0, 0]]
+
+
+def test_vtransform_matches_reference_source(golden_dir):
+    """get_geometry + the bev_pool index glue, pinned to a fixture produced by exec'ing the
+    reference's own vtransforms/base.py on the CPU (tests/golden/make_golden.py::gen_vtransform)."""
+    import torch
+    from bevfusion_b200 import synthetic as S
+    from bevfusion_b200.vtransform import create_frustum, gen_dx_bx, get_geometry
+    g = np.load(os.path.join(golden_dir, "vtransform_tiny.npz"))
+    cfg = S.CONFIGS["tiny"]
+    frustum = create_frustum(cfg["image_size"], cfg["feature_size"], cfg["dbound"])
+    assert np.array_equal(frustum.numpy(), g["frustum"])                       # bit-exact frustum
+    dx, bx, nx = gen_dx_bx(cfg["xbound"], cfg["ybound"], cfg["zbound"])
+    assert np.array_equal(dx.numpy(), g["dx"]) and np.array_equal(bx.numpy(), g["bx"])
+    assert nx.tolist() == g["nx"].tolist()
+    rig = S.camera_rig(cfg["n_cam"], cfg["image_size"], batch=2)
+    geom = get_geometry(frustum, rig["camera2lidar_rots"], rig["camera2lidar_trans"], rig["intrins"],
+                        rig["post_rots"], rig["post_trans"], torch.from_numpy(g["extra_rots"]),
+                        torch.from_numpy(g["extra_trans"]))
+    assert np.array_equal(geom.numpy(), g["geom"])                             # same fp32 op chain
+    # oracle quantise + filter reproduces the coords the reference hands to the op, row for row
+    odx, obx, onx = oracle.gen_dx_bx(cfg["xbound"], cfg["ybound"], cfg["zbound"])
+    coords, kept = oracle.quantize_filter(g["geom"], odx, obx, onx, 2)
+    assert int(kept.sum()) == int(g["x_rows"])
+    assert np.array_equal(coords[kept], g["coords"])
+    B, D, H, W = (int(v) for v in g["dims"])
+    assert (B, D, H, W) == (2, int(onx[2]), int(onx[0]), int(onx[1]))

@@ -144,3 +144,23 @@ def test_stress_c5_voxel_grid(cuda):
     # every input feeds exactly one output through its parity-compatible offsets: pair count check
     pairs = int((rb2.nbr >= 0).sum())
     assert pairs >= coords.shape[0] and pairs <= 8 * coords.shape[0]
+
+
+def test_voxelize_batch_matches_reference_glue(cuda):
+    """voxelize_batch == the torch glue of BEVFusion.voxelize (bevfusion.py:169-197) on two samples."""
+    import torch.nn.functional as F
+    from bevfusion_b200 import synthetic as S
+    from bevfusion_b200.voxelize import Voxelization, voxelize_batch
+    vs, cr = [0.4, 0.5, 0.25], [-8.0, -6.0, -1.0, 8.0, 6.0, 3.0]
+    pts = [torch.from_numpy(S.uniform_cloud(n, seed=n, margin=0.5, rng_range=cr)).to(cuda) for n in (30000, 17000)]
+    vox = Voxelization(vs, cr, 10, (20000, 20000)).eval()
+    feats, coords, sizes = voxelize_batch(pts, vox)
+    rf, rc, rs = [], [], []
+    for k, p in enumerate(pts):                                # the reference's loop, verbatim semantics
+        f, c, n = vox(p)
+        rf.append(f); rc.append(F.pad(c, (1, 0), mode="constant", value=k)); rs.append(n)
+    rf, rc, rs = torch.cat(rf), torch.cat(rc), torch.cat(rs)
+    rf = rf.sum(dim=1, keepdim=False) / rs.type_as(rf).view(-1, 1)
+    assert torch.equal(coords, rc) and torch.equal(sizes, rs)
+    assert float((feats - rf).abs().max()) <= 1e-5 * float(rf.abs().max())
+    assert int(coords[:, 0].max()) == 1
