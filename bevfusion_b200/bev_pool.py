@@ -262,5 +262,7 @@ class BEVPoolPlan:
 
     def __call__(self, x):
         out = self.pool(x)                                  # [B, Z, X, Y, C]
-        out = out.permute(0, 4, 1, 2, 3).contiguous()       # bev_pool.py:97
-        return torch.cat(out.unbind(dim=2), 1)              # base.py:174 collapse Z
+        # bev_pool.py:97 permute(0,4,1,2,3).contiguous() followed by base.py:174
+        # cat(unbind(dim=2), 1) puts channel z*C + c at [b, :, x, y]: one permute-copy does both
+        B, Z, X, Y, C = out.shape
+        return out.permute(0, 1, 4, 2, 3).contiguous().view(B, Z * C, X, Y)

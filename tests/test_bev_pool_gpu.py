@@ -292,3 +292,21 @@ def test_prepare_vs_reference_vtransform_fixture(cuda, golden_dir):
     assert np.array_equal(t.ranks[:t.n_kept].cpu().numpy(), rs.astype(np.int32))
     assert np.array_equal(t.geom.cpu().numpy(), ref_coords[order].astype(np.int32))
     assert np.array_equal(t.starts.cpu().numpy(), starts) and np.array_equal(t.lengths.cpu().numpy(), lengths)
+
+
+def test_plan_layout_matches_reference_path_multi_z(cuda):
+    """plan(x) == BaseTransform.bev_pool(geom, x) (torch index glue + drop-in op + permute + cat)
+    on a grid with B = 2 samples and nz = 2 height bins."""
+    from bevfusion_b200 import synthetic as S
+    from bevfusion_b200.bev_pool import BEVPoolPlan
+    from bevfusion_b200.vtransform import LSSGeometry
+    cfg = dict(S.CONFIGS["tiny"]); cfg["zbound"] = (-10.0, 10.0, 10.0)
+    geom, _ = S.camera_geometry("tiny", batch=2, device=cuda)
+    lss = LSSGeometry(cfg["image_size"], cfg["feature_size"], cfg["xbound"], cfg["ybound"], cfg["zbound"],
+                      cfg["dbound"]).to(cuda)
+    x = S.lifted_features("tiny", batch=2, device=cuda, seed=3)
+    ref = lss.bev_pool_reference_path(geom, x)                  # [2, 80*2, 64, 64]
+    plan = BEVPoolPlan(geom, cfg["xbound"], cfg["ybound"], cfg["zbound"])
+    out = plan(x)
+    assert tuple(out.shape) == tuple(ref.shape) == (2, 160, 64, 64)
+    assert float((out - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
