@@ -383,7 +383,26 @@ def run_ours(args, rank, world, local_rank):
         "roofline_encoder": roof_enc, "roofline_voxelize": roof_vox,
         "cpu_baseline": cpu, "clocks": clocks,
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Route fd 1 to stderr while the job runs (NCCL prints its version banner to stdout) so that
+    stdout carries exactly ONE line: the JSON emitted by emit()."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line), flush=True)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -476,7 +495,7 @@ def run_reference(args, rank, world):
                              "sample": CPU_SAMPLE},
             "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
@@ -491,6 +510,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    quiet_stdout()
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
