@@ -26,6 +26,7 @@ _SIGNATURES = {
     "bevb200_bev_pool_grad": (c_int, [c_int] * 7 + [_P] * 6),
     "bevb200_bev_pool_perm": (c_int, [c_int] * 7 + [_P] * 7 + [c_size_t, _P]),
     "bevb200_bev_pool_grad_perm": (c_int, [c_int] * 8 + [_P] * 7),
+    "bevb200_bev_channels_first": (c_int, [_P, _P, c_int, c_int, c_int, c_int, ctypes.c_longlong, _P]),
     "bevb200_bev_pool_lift": (c_int, [c_int] * 7 + [_P, _P, c_int, c_int] + [_P] * 6 + [c_size_t, _P]),
     "bevb200_bev_pool_prepare_workspace_bytes": (c_size_t, [c_int]),
     "bevb200_bev_pool_prepare_geom": (c_int, [_P, c_int, c_int, _P, _P, _P, c_int] + [_P] * 7
@@ -34,6 +35,16 @@ _SIGNATURES = {
     "bevb200_hard_voxelize_workspace_bytes": (c_size_t, [c_int, c_int]),
     "bevb200_hard_voxelize": (c_int, [_P, c_int, c_int, _P, _P, c_int, c_int] + [_P] * 5
                               + [c_size_t, _P]),
+    "bevb200_hard_voxelize_mean": (c_int, [_P, c_int, c_int, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P,
+                                           _P, c_size_t, _P]),
+    "bevb200_depth_rasterize_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "bevb200_depth_rasterize": (c_int, [_P, c_int, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int,
+                                        c_int, _P, _P, c_size_t, _P]),
+    "bevb200_dynamic_scatter_workspace_bytes": (c_size_t, [c_int]),
+    "bevb200_dynamic_scatter": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P,
+                                        c_size_t, _P]),
+    "bevb200_dynamic_scatter_backward": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int,
+                                                 c_int, _P, _P]),
     "bevb200_dynamic_voxelize": (c_int, [_P, c_int, c_int, _P, _P, _P, _P]),
     "bevb200_voxel_mean": (c_int, [_P, _P, _P] + [c_int] * 4 + [_P, _P, _P]),
     "bevb200_rulebook_workspace_bytes": (c_size_t, [c_int, c_int, _P]),
@@ -50,7 +61,7 @@ _SIGNATURES = {
     "bevb200_rulebook_transpose": (c_int, [_P, c_int, c_int, c_int, _P, _P]),
     "bevb200_spconv_backward_workspace_bytes": (c_size_t, [c_int] * 3),
     "bevb200_spconv_backward": (c_int, [_P] * 5 + [c_int] * 6 + [_P, _P, _P, c_size_t, _P]),
-    "bevb200_sparse_to_dense": (c_int, [_P, _P, c_int, c_int, c_int, _P, c_int, _P, _P]),
+    "bevb200_sparse_to_dense": (c_int, [_P, _P, c_int, c_int, c_int, _P, c_int, ctypes.c_longlong, _P, _P]),
 }
 
 

@@ -260,9 +260,23 @@ class BEVPoolPlan:
         _C.check(rc, "bev_pool_lift")
         return out
 
-    def __call__(self, x):
-        out = self.pool(x)                                  # [B, Z, X, Y, C]
+    def __call__(self, x, out=None):
+        """pool + module output layout.  `out` (optional) is a [B, Z*C, X, Y] float32 view that is
+        dense inside each batch item -- e.g. the camera channels of the fuser's concatenated
+        input (fusers/conv.py:16) -- and is written in place."""
+        pooled = self.pool(x)                               # [B, Z, X, Y, C]
         # bev_pool.py:97 permute(0,4,1,2,3).contiguous() followed by base.py:174
-        # cat(unbind(dim=2), 1) puts channel z*C + c at [b, :, x, y]: one permute-copy does both
-        B, Z, X, Y, C = out.shape
-        return out.permute(0, 1, 4, 2, 3).contiguous().view(B, Z * C, X, Y)
+        # cat(unbind(dim=2), 1) puts channel z*C + c at [b, :, x, y]: one tiled transpose does both
+        B, Z, X, Y, C = pooled.shape
+        if pooled.requires_grad:
+            res = pooled.permute(0, 1, 4, 2, 3).contiguous().view(B, Z * C, X, Y)
+            return res if out is None else out.copy_(res)
+        from .spconv.ops import _batch_stride_of
+        with torch.cuda.device(pooled.device):
+            if out is None:
+                out = torch.empty((B, Z * C, X, Y), dtype=pooled.dtype, device=pooled.device)
+            stride = _batch_stride_of(out, (B, Z * C, X, Y))
+            rc = _C.lib().bevb200_bev_channels_first(_C.ptr(pooled), _C.ptr(out), B, Z, X * Y, C, stride,
+                                                     _C.current_stream(pooled.device))
+        _C.check(rc, "bev_channels_first")
+        return out

@@ -514,6 +514,30 @@ __global__ void bevpool_fwd_tma_fixup_kernel(const int32_t *__restrict__ starts,
   }
 }
 
+// [rows, C] -> [C, rows] tiled transpose (32 x 32 tiles through padded shared memory): turns the op
+// layout [B, Z, X, Y, C] into the module output [B, Z*C, X, Y] (bev_pool.py:97 + base.py:174)
+__global__ void __launch_bounds__(256)
+    bev_channels_first_kernel(const float *__restrict__ in, float *__restrict__ out, int rows, int c,
+                              int nz, long long out_batch_stride) {
+  __shared__ float tile[32][33];
+  const long long slab = blockIdx.z;                       // (b, z) slab of X*Y rows
+  const float *src = in + slab * (long long)rows * c;
+  float *dst = out + (slab / nz) * out_batch_stride + (slab % nz) * (long long)rows * c;
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int r = r0 + ty + i, cc = c0 + tx;
+    tile[ty + i][tx] = (r < rows && cc < c) ? src[(long long)r * c + cc] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int cc = c0 + ty + i, r = r0 + tx;
+    if (cc < c && r < rows) dst[(long long)cc * rows + r] = tile[tx][ty + i];
+  }
+}
+
 // any channel count: one thread per (interval, channel), like the reference kernel but on the
 // caller's stream and with bounds checks.  Used only when C is not one of the tuned widths.
 __global__ void bevpool_fwd_generic_kernel(const float *__restrict__ x,
@@ -1072,6 +1096,18 @@ int bevb200_bev_pool_lift(int b, int d, int h, int w, int n, int c, int n_interv
                                                  out, workspace, zfill, st, depth, lift)
   BEVB200_POOL_DISPATCH(c, CALL_LIFT, BEVB200_REQUIRE(false, "bev_pool_lift: channel count not in {16,32,64,80,96,128,160,256}"));
 #undef CALL_LIFT
+  return BEVB200_OK;
+}
+
+int bevb200_bev_channels_first(const float *in, float *out, int batch, int nz, int rows, int c,
+                               long long out_batch_stride, void *stream) {
+  BEVB200_REQUIRE(batch > 0 && nz > 0 && rows > 0 && c > 0 && in && out, "bad argument");
+  BEVB200_REQUIRE((long long)batch * nz <= 65535, "too many (batch, z) slabs");
+  if (out_batch_stride == 0) out_batch_stride = (long long)nz * rows * c;
+  BEVB200_REQUIRE(out_batch_stride >= (long long)nz * rows * c, "output batch stride too small");
+  dim3 grid((rows + 31) / 32, (c + 31) / 32, batch * nz);
+  BEVB200_LAUNCH(bev_channels_first_kernel, grid, 256, 0, (cudaStream_t)stream, in, out, rows, c, nz,
+                 out_batch_stride);
   return BEVB200_OK;
 }
 

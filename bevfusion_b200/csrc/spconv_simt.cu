@@ -166,7 +166,7 @@ int spconv_forward_simt(const float *features, const float *weight, const int32_
 __global__ void sparse_to_dense_kernel(const float *__restrict__ features,
                                        const int32_t *__restrict__ indices, int n, int c,
                                        int batch, int X, int Y, int Z, int z_major,
-                                       float *__restrict__ out) {
+                                       long long out_batch_stride, float *__restrict__ out) {
   const long long total = (long long)n * c;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
        t += (long long)gridDim.x * blockDim.x) {
@@ -175,10 +175,9 @@ __global__ void sparse_to_dense_kernel(const float *__restrict__ features,
     if ((unsigned)p.x >= (unsigned)batch || (unsigned)p.y >= (unsigned)X ||
         (unsigned)p.z >= (unsigned)Y || (unsigned)p.w >= (unsigned)Z)
       continue;
-    long long dst = z_major
-                        ? ((((long long)p.x * c + ch) * Z + p.w) * X + p.y) * Y + p.z
-                        : ((((long long)p.x * c + ch) * X + p.y) * Y + p.z) * Z + p.w;
-    out[dst] = features[(long long)i * c + ch];
+    long long dst = z_major ? (((long long)ch * Z + p.w) * X + p.y) * Y + p.z
+                            : (((long long)ch * X + p.y) * Y + p.z) * Z + p.w;
+    out[p.x * out_batch_stride + dst] = features[(long long)i * c + ch];
   }
 }
 
@@ -249,17 +248,24 @@ int bevb200_spconv_forward_packed(const float *features, const float *packed_wei
 
 int bevb200_sparse_to_dense(const float *features, const int32_t *indices, int n, int c,
                             int batch_size, const int32_t *spatial_shape_host, int z_major,
-                            float *out, void *stream) {
+                            long long out_batch_stride, float *out, void *stream) {
   BEVB200_REQUIRE(n >= 0 && c > 0 && batch_size > 0 && spatial_shape_host && out, "bad argument");
   const int X = spatial_shape_host[0], Y = spatial_shape_host[1], Z = spatial_shape_host[2];
   BEVB200_REQUIRE(X > 0 && Y > 0 && Z > 0, "bad spatial shape");
   cudaStream_t st = (cudaStream_t)stream;
-  size_t bytes = (size_t)batch_size * c * X * Y * Z * sizeof(float);
-  BEVB200_CUDA(cudaMemsetAsync(out, 0, bytes, st));
+  const long long per_batch = (long long)c * X * Y * Z;
+  if (out_batch_stride == 0) out_batch_stride = per_batch;
+  BEVB200_REQUIRE(out_batch_stride >= per_batch, "output batch stride too small");
+  if (out_batch_stride == per_batch) {
+    BEVB200_CUDA(cudaMemsetAsync(out, 0, (size_t)batch_size * per_batch * sizeof(float), st));
+  } else {  // channel slice of a wider [B, C_total, ...] buffer (the fuser's concatenated input)
+    BEVB200_CUDA(cudaMemset2DAsync(out, (size_t)out_batch_stride * sizeof(float), 0,
+                                   (size_t)per_batch * sizeof(float), batch_size, st));
+  }
   if (n == 0) return BEVB200_OK;
   BEVB200_REQUIRE(features && indices, "null argument");
   BEVB200_LAUNCH(sparse_to_dense_kernel, grid_for((long long)n * c, 256), 256, 0, st, features,
-                 indices, n, c, batch_size, X, Y, Z, z_major, out);
+                 indices, n, c, batch_size, X, Y, Z, z_major, out_batch_stride, out);
   return BEVB200_OK;
 }
 

@@ -163,6 +163,48 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// K5' (fused): the voxel's first point sums the rows named by the list (slot order), divides by
+// the count and writes the mean row + (batch, x, y, z): voxelize + `feats.sum(dim=1) / sizes` +
+// `F.pad(coords, (1, 0), value=k)` (bevfusion.py:178-195) without the [M, P, F] intermediate.
+__global__ void __launch_bounds__(256)
+    vox_mean_kernel(const float *__restrict__ points, int n, int nf, VoxParams vp, int P,
+                    int max_voxels, int batch_idx, const int32_t *__restrict__ point_pvid,
+                    const int32_t *__restrict__ lists, const int32_t *__restrict__ counts,
+                    const uint32_t *__restrict__ first_bits,
+                    const uint32_t *__restrict__ word_prefix,
+                    const uint32_t *__restrict__ total_voxels, float *__restrict__ feats,
+                    int32_t *__restrict__ coords4, int32_t *__restrict__ num_points,
+                    int32_t *__restrict__ voxel_num) {
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    *voxel_num = (int32_t)min(*total_voxels, (uint32_t)max_voxels);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int pv = point_pvid[i];
+    if (pv < 0) continue;
+    const int32_t *a = lists + (long long)pv * P;
+    if (a[0] != i) continue;  // only the voxel's first point works
+    int vid = (int)(word_prefix[i >> 5] + __popc(first_bits[i >> 5] & ((1u << (i & 31)) - 1)));
+    if (vid >= max_voxels) continue;
+    const int cnt = min(counts[pv], P);
+    float acc[8];
+    const int nfc = min(nf, 8);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (int s = 0; s < cnt; ++s) {
+      const float *src = points + (long long)a[s] * nf;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (k < nfc) acc[k] = __fadd_rn(acc[k], src[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (k < nfc) feats[(long long)vid * nf + k] = __fdiv_rn(acc[k], (float)cnt);
+    int c[3];
+    point_coords(points + (long long)i * nf, vp, c);
+    *reinterpret_cast<int4 *>(coords4 + 4ll * vid) = make_int4(batch_idx, c[0], c[1], c[2]);
+    if (num_points) num_points[vid] = cnt;
+  }
+}
+
 __global__ void dynamic_voxelize_kernel(const float *__restrict__ points, int n, int nf,
                                         VoxParams vp, int32_t *__restrict__ coors) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -248,6 +290,35 @@ size_t bevb200_hard_voxelize_workspace_bytes(int num_points, int max_points) {
   return vox_layout(num_points, max_points, nullptr, 0, nullptr);
 }
 
+// K1-K4, shared by the plain and the mean-fused entry points
+static int vox_front(const char *who, const float *points, int n, int num_features,
+                     const VoxParams &vp, int max_points, void *workspace, size_t workspace_bytes,
+                     cudaStream_t st, VoxWs *wout) {
+  VoxWs w;
+  size_t need = vox_layout(n, max_points, workspace, workspace_bytes, &w);
+  if (workspace == nullptr || workspace_bytes < need) {
+    snprintf(g_last_error, sizeof(g_last_error), "%s: workspace too small (%zu < %zu)", who,
+             workspace_bytes, need);
+    return BEVB200_EWORKSPACE;
+  }
+  // keys = empty (0xff..), lists = 0x7f7f7f7f, counts / counters = 0: the three regions are
+  // laid out back to back in that order (see vox_layout)
+  BEVB200_CUDA(cudaMemsetAsync(w.keys, 0xff, (size_t)w.table_size * sizeof(unsigned long long), st));
+  BEVB200_CUDA(cudaMemsetAsync(w.lists, 0x7f, (size_t)n * max_points * sizeof(int32_t), st));
+  BEVB200_CUDA(cudaMemsetAsync(w.counts, 0, (char *)w.slot_pvid - (char *)w.counts, st));
+  const int grid = grid_for(n, 256);
+  BEVB200_LAUNCH(vox_insert_kernel, grid, 256, 0, st, points, n, num_features, vp, w.keys,
+                 w.slot_pvid, w.table_size - 1, w.point_slot, w.pvid_counter);
+  BEVB200_LAUNCH(vox_rank_kernel, grid, 256, 0, st, n, max_points, w.point_slot, w.slot_pvid,
+                 w.point_pvid, w.lists, w.counts);
+  BEVB200_LAUNCH(vox_flags_kernel, grid, 256, 0, st, n, max_points, w.point_pvid, w.lists,
+                 w.first_bits);
+  int rc = exclusive_scan_u32(w.first_bits, w.word_prefix, w.nwords, w.tiles, w.total, true, st);
+  if (rc) return rc;
+  *wout = w;
+  return BEVB200_OK;
+}
+
 int bevb200_hard_voxelize(const float *points, int num_points, int num_features,
                           const float *voxel_size_host, const float *coors_range_host,
                           int max_points, int max_voxels, float *voxels, int32_t *coors,
@@ -266,29 +337,40 @@ int bevb200_hard_voxelize(const float *points, int num_points, int num_features,
   }
   BEVB200_REQUIRE(points && voxels && coors && num_points_per_voxel, "null argument");
   VoxWs w;
-  size_t need = vox_layout(n, max_points, workspace, workspace_bytes, &w);
-  if (workspace == nullptr || workspace_bytes < need) {
-    snprintf(g_last_error, sizeof(g_last_error), "hard_voxelize: workspace too small (%zu < %zu)",
-             workspace_bytes, need);
-    return BEVB200_EWORKSPACE;
-  }
-  // keys = empty (0xff..), lists = 0x7f7f7f7f, counts / counters = 0: the three regions are
-  // laid out back to back in that order (see vox_layout)
-  BEVB200_CUDA(cudaMemsetAsync(w.keys, 0xff, (size_t)w.table_size * sizeof(unsigned long long), st));
-  BEVB200_CUDA(cudaMemsetAsync(w.lists, 0x7f, (size_t)n * max_points * sizeof(int32_t), st));
-  BEVB200_CUDA(cudaMemsetAsync(w.counts, 0, (char *)w.slot_pvid - (char *)w.counts, st));
-  const int grid = grid_for(n, 256);
-  BEVB200_LAUNCH(vox_insert_kernel, grid, 256, 0, st, points, n, num_features, vp, w.keys,
-                 w.slot_pvid, w.table_size - 1, w.point_slot, w.pvid_counter);
-  BEVB200_LAUNCH(vox_rank_kernel, grid, 256, 0, st, n, max_points, w.point_slot, w.slot_pvid,
-                 w.point_pvid, w.lists, w.counts);
-  BEVB200_LAUNCH(vox_flags_kernel, grid, 256, 0, st, n, max_points, w.point_pvid, w.lists,
-                 w.first_bits);
-  int rc = exclusive_scan_u32(w.first_bits, w.word_prefix, w.nwords, w.tiles, w.total, true, st);
+  int rc = vox_front("hard_voxelize", points, n, num_features, vp, max_points, workspace,
+                     workspace_bytes, st, &w);
   if (rc) return rc;
-  BEVB200_LAUNCH(vox_scatter_kernel, grid, 256, 0, st, points, n, num_features, vp, max_points,
-                 max_voxels, w.point_pvid, w.lists, w.counts, w.first_bits, w.word_prefix, w.total,
-                 voxels, coors, num_points_per_voxel, voxel_num);
+  BEVB200_LAUNCH(vox_scatter_kernel, grid_for(n, 256), 256, 0, st, points, n, num_features, vp,
+                 max_points, max_voxels, w.point_pvid, w.lists, w.counts, w.first_bits, w.word_prefix,
+                 w.total, voxels, coors, num_points_per_voxel, voxel_num);
+  return BEVB200_OK;
+}
+
+int bevb200_hard_voxelize_mean(const float *points, int num_points, int num_features,
+                               const float *voxel_size_host, const float *coors_range_host,
+                               int max_points, int max_voxels, int batch_idx, float *feats,
+                               int32_t *coords4, int32_t *num_points_per_voxel, int32_t *voxel_num,
+                               void *workspace, size_t workspace_bytes, void *stream) {
+  BEVB200_REQUIRE(num_points >= 0 && num_features >= 3 && num_features <= 8, "bad point tensor shape");
+  BEVB200_REQUIRE(max_points > 0 && max_voxels > 0, "max_points / max_voxels must be positive");
+  BEVB200_REQUIRE(voxel_size_host && coors_range_host && voxel_num, "null argument");
+  VoxParams vp;
+  BEVB200_REQUIRE(make_params(voxel_size_host, coors_range_host, &vp) == 0, "bad voxel grid");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = num_points;
+  if (n == 0) {
+    BEVB200_CUDA(cudaMemsetAsync(voxel_num, 0, sizeof(int32_t), st));
+    return BEVB200_OK;
+  }
+  BEVB200_REQUIRE(points && feats && coords4, "null argument");
+  BEVB200_REQUIRE((uintptr_t)coords4 % 16 == 0, "coords must be 16-byte aligned");
+  VoxWs w;
+  int rc = vox_front("hard_voxelize_mean", points, n, num_features, vp, max_points, workspace,
+                     workspace_bytes, st, &w);
+  if (rc) return rc;
+  BEVB200_LAUNCH(vox_mean_kernel, grid_for(n, 256), 256, 0, st, points, n, num_features, vp,
+                 max_points, max_voxels, batch_idx, w.point_pvid, w.lists, w.counts, w.first_bits,
+                 w.word_prefix, w.total, feats, coords4, num_points_per_voxel, voxel_num);
   return BEVB200_OK;
 }
 

@@ -45,18 +45,23 @@ class SparseEncoder(nn.Module):
                                                norm_cfg=norm_cfg, padding=0,
                                                indice_key="spconv_down2", conv_type="SparseConv3d")
 
-    def forward(self, voxel_features, coors, batch_size, fused=None, precision=None, **kwargs):
+    def forward(self, voxel_features, coors, batch_size, fused=None, precision=None, out=None,
+                **kwargs):
         """sparse_encoder.py:99-132.  voxel_features [N, C] fp32, coors [N, 4] int32
         (batch, x, y, z).  Returns spatial features [B, C*D, H, W].
 
         fused=None picks the fused path (BN / ReLU / residual in the conv epilogues, dense()
-        written directly in the output layout) whenever the module is in eval mode."""
+        written directly in the output layout) whenever the module is in eval mode.  `out`
+        (fused path) is an optional [B, C*D, H, W] view to write into, e.g. the LiDAR channels
+        of the fuser's concatenated input (fusers/conv.py:16)."""
         coors = coors.int()
         if fused is None:
             fused = not self.training and self.order == ("conv", "norm", "act")
         x = spconv.SparseConvTensor(voxel_features, coors, self.sparse_shape, batch_size)
         if fused:
-            return self._forward_fused(x, precision)
+            return self._forward_fused(x, precision, out)
+        if out is not None:
+            raise ValueError("out= is only supported on the fused (eval) path")
         x = self.conv_input(x)
         encode_features = []
         for encoder_layer in self.encoder_layers:
@@ -74,7 +79,7 @@ class SparseEncoder(nn.Module):
         s, t = bn_scale_shift(bn)
         return conv(x, scale=s, shift=t, relu=True, precision=precision)
 
-    def _forward_fused(self, x, precision):
+    def _forward_fused(self, x, precision, dense_out=None):
         x = self._convmodule_fused(self.conv_input, x, precision)
         for stage in self.encoder_layers:
             for block in stage:
@@ -85,7 +90,7 @@ class SparseEncoder(nn.Module):
         out = self._convmodule_fused(self.conv_out, x, precision)
         # dense() + permute(0,1,4,2,3) + view(N, C*D, H, W) in one kernel
         return sp_ops.sparse_to_dense(out.features, out.indices, int(out.batch_size),
-                                      out.spatial_shape, z_major=True)
+                                      out.spatial_shape, z_major=True, out=dense_out)
 
     def make_encoder_layers(self, make_block, norm_cfg, in_channels, block_type="conv_module",
                             conv_cfg=dict(type="SubMConv3d")):

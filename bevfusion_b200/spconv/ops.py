@@ -353,9 +353,23 @@ class _SparseConvExt:
 sparse_conv_ext = _SparseConvExt()
 
 
-def sparse_to_dense(features, indices, batch_size, spatial_shape, z_major=False):
+def _batch_stride_of(out, shape):
+    """`out` must be a [B, C, ...] view that is dense inside each batch item (a channel slice
+    of a wider channels-first buffer qualifies); returns its batch stride in elements."""
+    if tuple(out.shape) != tuple(shape) or out.dtype != torch.float32:
+        raise ValueError(f"out must be float32 of shape {tuple(shape)}")
+    inner = 1
+    for size, stride in zip(reversed(out.shape[1:]), reversed(out.stride()[1:])):
+        if size != 1 and stride != inner:
+            raise ValueError("out must be contiguous inside each batch item")
+        inner *= size
+    return int(out.stride(0)) if out.shape[0] > 1 else inner
+
+
+def sparse_to_dense(features, indices, batch_size, spatial_shape, z_major=False, out=None):
     """dense() of a sparse tensor, channels first (structure.py:49-59); z_major=True gives the
-    SparseEncoder output layout [B, C*Z, X, Y] directly (sparse_encoder.py:126-130)."""
+    SparseEncoder output layout [B, C*Z, X, Y] directly (sparse_encoder.py:126-130).  `out`
+    may be a channel slice of the fuser's concatenated input (fusers/conv.py:16)."""
     _C.require_cuda(features, "features", torch.float32)
     _C.require_cuda(indices, "indices", torch.int32)
     n, c = features.shape
@@ -363,9 +377,11 @@ def sparse_to_dense(features, indices, batch_size, spatial_shape, z_major=False)
     dev = features.device
     with torch.cuda.device(dev):
         shape = (batch_size, c * Z, X, Y) if z_major else (batch_size, c, X, Y, Z)
-        out = torch.empty(shape, dtype=torch.float32, device=dev)
+        if out is None:
+            out = torch.empty(shape, dtype=torch.float32, device=dev)
+        stride = _batch_stride_of(out, shape)
         rc = _C.lib().bevb200_sparse_to_dense(_C.ptr(features), _C.ptr(indices), n, c, int(batch_size),
-                                              _vp(_i32([X, Y, Z])), int(bool(z_major)), _C.ptr(out),
-                                              _C.current_stream(dev))
+                                              _vp(_i32([X, Y, Z])), int(bool(z_major)), stride,
+                                              _C.ptr(out), _C.current_stream(dev))
     _C.check(rc, "sparse_to_dense")
     return out

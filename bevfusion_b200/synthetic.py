@@ -59,6 +59,38 @@ def camera_rig(n_cam=6, image_size=(256, 704), batch=1):
                 post_rots=st(prot), post_trans=st(ptr))
 
 
+def lidar_camera_matrices(n_cam=6, image_size=(256, 704), batch=1, augment=True):
+    """4x4 matrices the depth-aware lift consumes (base.py:237-262), consistent with camera_rig:
+    lidar2image = K @ inverse(camera2lidar), img_aug_matrix from the resize / crop, and a
+    per-sample lidar augmentation (z rotation, scale, translation).  [B, N, 4, 4] / [B, 4, 4] fp32."""
+    rig = camera_rig(n_cam, image_size, batch)
+    B, N = batch, n_cam
+    eye = torch.eye(4).view(1, 1, 4, 4).repeat(B, N, 1, 1)
+    cam2lidar = eye.clone()
+    cam2lidar[..., :3, :3] = rig["camera2lidar_rots"]
+    cam2lidar[..., :3, 3] = rig["camera2lidar_trans"]
+    lidar2cam = torch.inverse(cam2lidar)
+    K = eye.clone()
+    K[..., :3, :3] = rig["intrins"]
+    lidar2image = K.matmul(lidar2cam)
+    img_aug = eye.clone()
+    img_aug[..., :3, :3] = rig["post_rots"]
+    img_aug[..., :3, 3] = rig["post_trans"]
+    lidar_aug = torch.eye(4).view(1, 4, 4).repeat(B, 1, 1)
+    if augment:
+        for b in range(B):
+            a = 0.1 - 0.17 * b
+            sc = 1.0 + 0.05 * (b + 1)
+            lidar_aug[b, :3, :3] = sc * torch.tensor([[math.cos(a), -math.sin(a), 0.0],
+                                                      [math.sin(a), math.cos(a), 0.0], [0.0, 0.0, 1.0]])
+            lidar_aug[b, :3, 3] = torch.tensor([0.5 - b, -0.25 + 0.5 * b, 0.1 * b])
+    out = dict(rig)
+    out.update(lidar2image=lidar2image.float().contiguous(), img_aug_matrix=img_aug.float().contiguous(),
+               lidar_aug_matrix=lidar_aug.float().contiguous(), camera2lidar=cam2lidar.float().contiguous(),
+               lidar2camera=lidar2cam.float().contiguous(), cam_intrinsic=K.float().contiguous())
+    return out
+
+
 def camera_geometry(cfg_name="C2", batch=1, device="cpu"):
     """(geom [B, N, D, fH, fW, 3] fp32, cfg dict) for one of CONFIGS."""
     cfg = CONFIGS[cfg_name]

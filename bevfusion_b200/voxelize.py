@@ -16,7 +16,8 @@ from torch.nn.modules.utils import _pair
 
 from . import _C
 
-__all__ = ["voxel_layer", "voxelization", "Voxelization", "voxelize_mean"]
+__all__ = ["voxel_layer", "voxelization", "Voxelization", "voxelize_mean", "voxelize_mean_fused",
+           "voxelize_batch"]
 
 
 def _floats(vals, n):
@@ -24,6 +25,68 @@ def _floats(vals, n):
     if len(vals) != n:
         raise ValueError("expected %d values, got %d" % (n, len(vals)))
     return _C.host_array(ctypes.c_float, vals)
+
+_REDUCE = {"sum": 0, "mean": 1, "max": 2}      # voxelization.h:12-22 convert_reduce_type
+
+
+def _reduce_code(reduce_type):
+    if reduce_type not in _REDUCE:
+        raise ValueError("do not support reduce type " + str(reduce_type))
+    return _REDUCE[reduce_type]
+
+
+def _dynamic_scatter_forward(feats, coors, reduce_type):
+    code = _reduce_code(reduce_type)
+    _C.require_cuda(feats, "feats", torch.float32)
+    _C.require_cuda(coors, "coors", torch.int32)
+    n, c = feats.shape
+    ndim = coors.shape[1]
+    if coors.shape[0] != n:
+        raise ValueError("feats and coors must have the same number of rows")
+    dev = feats.device
+    if n == 0:                                   # scatter_points_cuda.cu:196-200
+        return (feats.clone().detach(), coors.clone().detach(),
+                coors.new_empty((0,), dtype=torch.int32), coors.new_empty((0,), dtype=torch.int32), None)
+    with torch.cuda.device(dev):
+        reduced = torch.empty((n, c), dtype=torch.float32, device=dev)
+        out_coors = torch.empty((n, ndim), dtype=torch.int32, device=dev)
+        coors_map = torch.empty((n,), dtype=torch.int32, device=dev)
+        count = torch.empty((n,), dtype=torch.int32, device=dev)
+        reduce_from = torch.empty((n, c), dtype=torch.int32, device=dev) if code == 2 else None
+        meta = torch.empty((2,), dtype=torch.int32, device=dev)
+        nbytes = _C.lib().bevb200_dynamic_scatter_workspace_bytes(n)
+        ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=dev)
+        rc = _C.lib().bevb200_dynamic_scatter(
+            _C.ptr(feats), _C.ptr(coors), n, c, ndim, code, _C.ptr(reduced), _C.ptr(out_coors),
+            _C.ptr(coors_map), _C.ptr(count), _C.ptr(reduce_from), _C.ptr(meta), _C.ptr(ws), ws.numel(),
+            _C.current_stream(dev))
+    _C.check(rc, "dynamic_scatter")
+    m, too_big = (int(v) for v in meta.tolist())
+    if too_big:
+        raise ValueError("%d coordinate rows exceed the key range (2^20 per column, 2^15 with 4 columns)"
+                         % too_big)
+    return (reduced[:m], out_coors[:m], coors_map, count[:m],
+            reduce_from[:m] if reduce_from is not None else None)
+
+
+def _dynamic_scatter_backward(grad_feats, grad_reduced, feats, reduced, coors_map, count, reduce_type,
+                              reduce_from):
+    code = _reduce_code(reduce_type)
+    _C.require_cuda(grad_feats, "grad_feats", torch.float32)
+    _C.require_cuda(grad_reduced, "grad_reduced_feats", torch.float32)
+    n, c = grad_feats.shape
+    m = grad_reduced.shape[0]
+    dev = grad_feats.device
+    with torch.cuda.device(dev):
+        valid = reduce_from is not None
+        if code == 2 and not valid:
+            _C.require_cuda(feats, "feats", torch.float32)
+            _C.require_cuda(reduced, "reduced_feats", torch.float32)
+            reduce_from = torch.empty((max(m, 1), c), dtype=torch.int32, device=dev)
+        rc = _C.lib().bevb200_dynamic_scatter_backward(
+            _C.ptr(grad_reduced), _C.ptr(feats), _C.ptr(reduced), _C.ptr(coors_map), _C.ptr(count),
+            _C.ptr(reduce_from), int(valid), n, m, c, code, _C.ptr(grad_feats), _C.current_stream(dev))
+    _C.check(rc, "dynamic_scatter_backward")
 
 
 class _VoxelLayer:
@@ -71,12 +134,20 @@ class _VoxelLayer:
         _C.check(rc, "dynamic_voxelize")
 
     @staticmethod
-    def dynamic_point_to_voxel_forward(*args, **kwargs):
-        raise NotImplementedError("DynamicScatter is outside the hot path (SURVEY.md section 8f)")
+    def dynamic_point_to_voxel_forward(feats, coors, reduce_type="max"):
+        """voxelization.h:97-109 / scatter_points_cuda.cu:187-241.  Returns
+        [reduced_feats [M, C], out_coors [M, ndim], coors_map [N] int32, reduce_count [M] int32];
+        voxels are the unique coordinate rows in lexicographic order, rows with a negative
+        entry are dropped (coors_map -1)."""
+        out = _dynamic_scatter_forward(feats, coors, reduce_type)
+        return [out[0], out[1], out[2], out[3]]
 
     @staticmethod
-    def dynamic_point_to_voxel_backward(*args, **kwargs):
-        raise NotImplementedError("DynamicScatter is outside the hot path (SURVEY.md section 8f)")
+    def dynamic_point_to_voxel_backward(grad_feats, grad_reduced_feats, feats, reduced_feats,
+                                        coors_map, reduce_count, reduce_type="max"):
+        """voxelization.h:111-127 / scatter_points_cuda.cu:243-315: fills grad_feats in place."""
+        _dynamic_scatter_backward(grad_feats, grad_reduced_feats, feats, reduced_feats, coors_map,
+                                  reduce_count, reduce_type, None)
 
 
 voxel_layer = _VoxelLayer()
@@ -152,6 +223,30 @@ def voxelize_mean(voxels, coors, num_points, batch_idx=0):
     return feats, coords4
 
 
+def voxelize_mean_fused(points, voxel_size, coors_range, max_points, max_voxels, batch_idx=0):
+    """hard voxelization + per-voxel mean + (batch, x, y, z) coords in one pass over the points
+    (bevfusion.py:178-195 with voxelize_reduce), never materialising the [M, max_points, F]
+    voxel tensor.  Returns (feats [M, F], coords [M, 4] int32, num_points [M] int32)."""
+    _C.require_cuda(points, "points", torch.float32)
+    n, f = points.shape
+    vs, cr = _floats(voxel_size, 3), _floats(coors_range, 6)
+    dev = points.device
+    with torch.cuda.device(dev):
+        feats = torch.empty((max_voxels, f), dtype=torch.float32, device=dev)
+        coords4 = torch.empty((max_voxels, 4), dtype=torch.int32, device=dev)
+        num = torch.empty((max_voxels,), dtype=torch.int32, device=dev)
+        voxel_num = torch.zeros(1, dtype=torch.int32, device=dev)
+        nbytes = _C.lib().bevb200_hard_voxelize_workspace_bytes(n, int(max_points))
+        ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=dev)
+        rc = _C.lib().bevb200_hard_voxelize_mean(
+            _C.ptr(points), n, f, ctypes.cast(vs, ctypes.c_void_p), ctypes.cast(cr, ctypes.c_void_p),
+            int(max_points), int(max_voxels), int(batch_idx), _C.ptr(feats), _C.ptr(coords4),
+            _C.ptr(num), _C.ptr(voxel_num), _C.ptr(ws), ws.numel(), _C.current_stream(dev))
+    _C.check(rc, "hard_voxelize_mean")
+    m = int(voxel_num.item())
+    return feats[:m], coords4[:m], num[:m]
+
+
 @torch.no_grad()
 def voxelize_batch(points, voxelize_module, voxelize_reduce=True):
     """BEVFusion.voxelize (mmdet3d/models/fusion_models/bevfusion.py:169-197): per-sample hard
@@ -160,7 +255,15 @@ def voxelize_batch(points, voxelize_module, voxelize_reduce=True):
 
     points: list of [N_k, F] CUDA tensors.  Returns (feats, coords [M, 4] int32 (b, x, y, z), sizes)."""
     feats, coords, sizes = [], [], []
+    hard = isinstance(voxelize_module, Voxelization) and voxelize_module.max_num_points > 0
     for k, res in enumerate(points):
+        if hard and voxelize_reduce:             # fused: no [M, P, F] intermediate
+            mv = voxelize_module.max_voxels[0 if voxelize_module.training else 1]
+            f, c4, n = voxelize_mean_fused(res.contiguous(), voxelize_module.voxel_size,
+                                           voxelize_module.point_cloud_range,
+                                           voxelize_module.max_num_points, mv, k)
+            feats.append(f); coords.append(c4); sizes.append(n)
+            continue
         ret = voxelize_module(res)
         if len(ret) == 3:
             f, c, n = ret

@@ -5,9 +5,57 @@ pooling itself goes through bevfusion_b200.bev_pool."""
 import torch
 from torch import nn
 
+from . import _C
 from .bev_pool import BEVPoolPlan, bev_pool, gen_dx_bx
 
-__all__ = ["gen_dx_bx", "create_frustum", "get_geometry", "LSSGeometry"]
+__all__ = ["gen_dx_bx", "create_frustum", "get_geometry", "LSSGeometry", "points_to_depth"]
+
+
+def points_to_depth(points, lidar2image, img_aug_matrix, lidar_aug_matrix, image_size,
+                    depth_input="scalar", depth_bins=None, add_depth_features=False,
+                    height_expand=False):
+    """The depth-image half of BaseDepthTransform.forward (base.py:266-329).
+
+    points: list of B [N_b, F] CUDA fp32 tensors (NOT modified -- the reference shifts their xyz in
+    place at :290); lidar2image / img_aug_matrix [B, ncam, 4, 4]; lidar_aug_matrix [B, 4, 4].
+    Returns depth [B, ncam, channels, iH, iW] with channels = (1 | depth_bins) (+ F).  Colliding
+    points: the largest point index wins (sequential index_put semantics)."""
+    if depth_input not in ("scalar", "one-hot"):
+        raise ValueError("depth_input must be 'scalar' or 'one-hot'")
+    one_hot = depth_input == "one-hot"
+    if one_hot and not depth_bins:
+        raise ValueError("one-hot depth needs depth_bins (the frustum's D)")
+    iH, iW = (int(v) for v in image_size)
+    B = len(points)
+    ncam = int(lidar2image.shape[1])
+    if height_expand:                                    # base.py:266-270 (radar pillars)
+        expanded = []
+        for p in points:
+            q = p.repeat_interleave(8, dim=0)
+            q[:, 2] = torch.arange(0.25, 2.25, 0.25, device=p.device).repeat(p.shape[0])
+            expanded.append(q)
+        points = expanded
+    dev = points[0].device
+    F = int(points[0].shape[1])
+    channels = (int(depth_bins) if one_hot else 1) + (F if add_depth_features else 0)
+    l2i = lidar2image.to(device=dev, dtype=torch.float32).contiguous()
+    ia = img_aug_matrix.to(device=dev, dtype=torch.float32).contiguous()
+    la = lidar_aug_matrix.to(device=dev, dtype=torch.float32).contiguous()
+    with torch.cuda.device(dev):
+        depth = torch.empty((B, ncam, channels, iH, iW), dtype=torch.float32, device=dev)
+        nbytes = _C.lib().bevb200_depth_rasterize_workspace_bytes(ncam, iH, iW)
+        ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=dev)
+        for b in range(B):
+            p = points[b]
+            _C.require_cuda(p, "points[%d]" % b, torch.float32)
+            if p.shape[1] != F:
+                raise ValueError("all samples must have the same number of point features")
+            rc = _C.lib().bevb200_depth_rasterize(
+                _C.ptr(p), int(p.shape[0]), F, _C.ptr(la[b]), _C.ptr(l2i[b]), _C.ptr(ia[b]), ncam, iH, iW,
+                int(one_hot), int(depth_bins or 0), int(bool(add_depth_features)), _C.ptr(depth[b]),
+                _C.ptr(ws), ws.numel(), _C.current_stream(dev))
+            _C.check(rc, "depth_rasterize")
+    return depth
 
 
 def create_frustum(image_size, feature_size, dbound):

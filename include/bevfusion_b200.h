@@ -98,6 +98,14 @@ BEVB200_API int bevb200_bev_pool_grad_perm(int b, int d, int h, int w, int n, in
                                const int32_t *geom_feats, const int32_t *interval_starts,
                                const int32_t *interval_lengths, float *x_grad, void *stream);
 
+/* Op layout [B, Z, X, Y, C] -> module layout [B, Z*C, X, Y] in one tiled transpose: replaces
+ * `x.permute(0, 4, 1, 2, 3).contiguous()` (bev_pool.py:97) + `torch.cat(x.unbind(dim=2), 1)`
+ * (base.py:174).  rows = X*Y.  out_batch_stride (floats; 0 = nz*rows*c) lets `out` be a channel
+ * slice of a wider [B, C_total, X, Y] buffer, i.e. the camera half of the fuser's concatenated
+ * input (fusers/conv.py:16 `torch.cat(inputs, dim=1)`) written in place. */
+BEVB200_API int bevb200_bev_channels_first(const float *in, float *out, int batch, int nz, int rows, int c,
+                                           long long out_batch_stride, void *stream);
+
 /* Fused LSS lift + pool ("next" row (f)1 of SURVEY.md section 8; BEVPoolv2-style): the lifted volume
  * x[p, :] = depth[p] * ctx[pixel(p), :] of LSSTransform / DepthLSSTransform.get_cam_feats
  * (mmdet3d/models/vtransforms/lss.py:68-73, depth_lss.py:92-97) is never materialised; the pooling
@@ -174,6 +182,20 @@ BEVB200_API int bevb200_hard_voxelize(const float *points, int num_points, int n
                           int32_t *num_points_per_voxel, int32_t *voxel_num,
                           void *workspace, size_t workspace_bytes, void *stream);
 
+/* Fused voxelize + mean-reduce + batch pad: what BEVFusion.voxelize does around the op when
+ * voxelize_reduce is on (mmdet3d/models/fusion_models/bevfusion.py:169-197 -- hard_voxelize, then
+ * `feats.sum(dim=1) / sizes` and `F.pad(coords, (1, 0), value=k)`), without materialising the
+ * [M, max_points, F] voxel tensor.  Same voxel order / caps as bevb200_hard_voxelize.
+ *   feats  [max_voxels, F] mean point row per voxel (slot-order fp32 sum, IEEE divide)
+ *   coords4 [max_voxels, 4] int32 (batch_idx, x, y, z), 16-byte aligned
+ *   num_points_per_voxel [max_voxels] (nullable), voxel_num device int32
+ * Rows >= voxel_num are left untouched.  F <= 8.  Workspace as bevb200_hard_voxelize. */
+BEVB200_API int bevb200_hard_voxelize_mean(const float *points, int num_points, int num_features,
+                               const float *voxel_size_host, const float *coors_range_host,
+                               int max_points, int max_voxels, int batch_idx, float *feats,
+                               int32_t *coords4, int32_t *num_points_per_voxel, int32_t *voxel_num,
+                               void *workspace, size_t workspace_bytes, void *stream);
+
 /* Replaces voxelization::dynamic_voxelize_gpu (voxelization_cuda.cu:485-528):
  * coors[i] = (cx, cy, cz) or (-1,-1,-1) when the point is out of range.  (The reference
  * kernel only guarantees coors[i][0] == -1 for such points, :38-47.) */
@@ -186,6 +208,53 @@ BEVB200_API int bevb200_dynamic_voxelize(const float *points, int num_points, in
 BEVB200_API int bevb200_voxel_mean(const float *voxels, const int32_t *coors, const int32_t *num_points,
                        int num_voxels, int max_points, int num_features, int batch_idx,
                        float *feats, int32_t *coords4, void *stream);
+
+/* ---- LiDAR depth images for the depth-aware camera lift ------------------------------------
+ * BaseDepthTransform.forward's per-sample loop (mmdet3d/models/vtransforms/base.py:279-329):
+ * undo the lidar augmentation, project every point into every camera with lidar2image, clamp z to
+ * [1e-5, 1e5], perspective divide, apply the image augmentation, keep points on the image and
+ * write their distance at (row, col).  Colliding points: the one with the LARGEST index wins (the
+ * sequential meaning of the reference's index_put; its CUDA result is arbitrary).
+ *   points [N, F] device fp32 (xyz first); lidar_aug_matrix [4,4], lidar2image [ncam,4,4],
+ *   img_aug_matrix [ncam,4,4]: device fp32 row-major, one sample.
+ *   one_hot == 0: channel 0 = distance ("scalar", :318-319); one_hot != 0: depth_bins channels,
+ *   1.0 at bin (long)min(dist, depth_bins-1) (:320-325).  add_features != 0 appends F channels
+ *   holding the winner's point row with xyz minus the lidar-aug translation (:327-329; the
+ *   reference has shifted them in place at :290 -- the caller's points are NOT modified here).
+ *   depth [ncam, channels, H, W] is fully written.  ncam <= 16. */
+BEVB200_API size_t bevb200_depth_rasterize_workspace_bytes(int ncam, int height, int width);
+BEVB200_API int bevb200_depth_rasterize(const float *points, int num_points, int num_features,
+                            const float *lidar_aug_matrix, const float *lidar2image,
+                            const float *img_aug_matrix, int ncam, int height, int width, int one_hot,
+                            int depth_bins, int add_features, float *depth, void *workspace,
+                            size_t workspace_bytes, void *stream);
+
+/* ---- DynamicScatter (mmdet3d/ops/voxel/src/scatter_points_cuda.cu:187-315; pybind
+ * `dynamic_point_to_voxel_forward / _backward`, voxelization.cpp:10-11) -----------------------
+ * reduce_type: 0 sum, 1 mean, 2 max (scatter_points_cuda.cu:7).
+ * Forward: rows of `coors` [N, ndim] (ndim 1..4; a row with a negative entry is dropped) name
+ * voxels; output voxels are the unique rows in lexicographic order (= at::unique_dim, :208).
+ *   reduced_feats [>=M, C], out_coors [>=M, ndim], coors_map [N] (voxel row or -1),
+ *   reduce_count [>=M], reduce_from [>=M, C] (nullable; arg-max point per (voxel, channel) for
+ *   the max backward), meta[2] device int32 = {M, number of rows with an entry too large for the
+ *   key (>= 2^20 for ndim <= 3, >= 2^15 for ndim 4; such rows are dropped and the caller should
+ *   raise)}.  Size the outputs for M = N.  Sums run in ascending point order: reproducible,
+ *   unlike the reference's float atomics. */
+BEVB200_API size_t bevb200_dynamic_scatter_workspace_bytes(int num_points);
+BEVB200_API int bevb200_dynamic_scatter(const float *feats, const int32_t *coors, int num_points,
+                            int num_features, int ndim, int reduce_type, float *reduced_feats,
+                            int32_t *out_coors, int32_t *coors_map, int32_t *reduce_count,
+                            int32_t *reduce_from, int32_t *meta, void *workspace,
+                            size_t workspace_bytes, void *stream);
+/* Backward (:243-315): grad_feats [N, C] is fully written.  For max, `reduce_from` [M, C] is
+ * used as given when reduce_from_valid != 0, else rebuilt by traceback from feats /
+ * reduced_feats (smallest point index attaining the maximum, :145-160). */
+BEVB200_API int bevb200_dynamic_scatter_backward(const float *grad_reduced_feats, const float *feats,
+                                     const float *reduced_feats, const int32_t *coors_map,
+                                     const int32_t *reduce_count, int32_t *reduce_from,
+                                     int reduce_from_valid, int num_points, int num_reduced,
+                                     int num_features, int reduce_type, float *grad_feats,
+                                     void *stream);
 
 /* ------------------------------------------------------------------------------------
  * sparse convolution (reference: mmdet3d/ops/spconv/include/spconv/spconv_ops.h,
@@ -309,10 +378,12 @@ BEVB200_API int bevb200_spconv_backward(const float *features, const float *weig
  * permute(0,1,4,2,3).view(N, C*D, H, W) (sparse_encoder.py:126-130):
  *   out[b, c*Z + z, x, y] = features[i, c] for indices[i] = (b, x, y, z); zero elsewhere.
  * With z_major == 0 the plain channels-first dense layout out[b, c, x, y, z] is written.
- * out must hold B*C*X*Y*Z floats; it is fully written (zero filled) by the call. */
+ * out must hold B*C*X*Y*Z floats; it is fully written (zero filled) by the call.
+ * out_batch_stride (floats; 0 = C*X*Y*Z) lets `out` be a channel slice of a wider
+ * [B, C_total, X, Y] buffer: the LiDAR half of the fuser input (fusers/conv.py:16) in place. */
 BEVB200_API int bevb200_sparse_to_dense(const float *features, const int32_t *indices, int n, int c,
                             int batch_size, const int32_t *spatial_shape_host, int z_major,
-                            float *out, void *stream);
+                            long long out_batch_stride, float *out, void *stream);
 
 #ifdef __cplusplus
 }

@@ -182,6 +182,131 @@ def voxel_mean(voxels, num_points):
     return (voxels.astype(np.float64).sum(axis=1) / num_points.reshape(-1, 1)).astype(np.float32)
 
 
+def dynamic_scatter(feats, coors, reduce_type="max"):
+    """dynamic_point_to_voxel_forward (scatter_points_cuda.cu:187-241): rows with a negative
+    entry are masked to -1 (:203), at::unique_dim sorts the rows lexicographically (:206-208) and
+    the leading all -1 row is removed (:210-215); features are reduced per voxel (sum / mean in
+    fp64 here, so the comparison with either GPU implementation is a tolerance one; max is exact).
+    Returns (reduced [M, C] f32, out_coors [M, ndim] i32, coors_map [N] i32, count [M] i32).
+    PINNING: the reference has no CPU path for this op (voxelization.h:118); the restatement is
+    checked on the GPU box against oracle/_ref's voxel_layer (tests/test_voxelize_gpu.py)."""
+    feats = np.asarray(feats, np.float32)
+    coors = np.asarray(coors, np.int32)
+    n, c = feats.shape
+    if n == 0:
+        return feats.copy(), coors.copy(), np.zeros(0, np.int32), np.zeros(0, np.int32)
+    clean = coors.copy()
+    clean[(coors < 0).any(1)] = -1
+    out_coors, inv, count = np.unique(clean, axis=0, return_inverse=True, return_counts=True)
+    inv = inv.reshape(-1).astype(np.int64)
+    if out_coors[0, 0] < 0:
+        out_coors, count, inv = out_coors[1:], count[1:], inv - 1
+    m = out_coors.shape[0]
+    keep = inv >= 0
+    if reduce_type == "max":
+        red = np.full((m, c), -np.inf, np.float32)
+        np.maximum.at(red, inv[keep], feats[keep])
+    else:
+        red = np.zeros((m, c), np.float64)
+        np.add.at(red, inv[keep], feats[keep].astype(np.float64))
+        if reduce_type == "mean":
+            red = red / count[:, None]
+        red = red.astype(np.float32)
+    return red, out_coors.astype(np.int32), inv.astype(np.int32), count.astype(np.int32)
+
+
+def dynamic_scatter_backward(grad_reduced, feats, reduced, coors_map, count, reduce_type="max"):
+    """dynamic_point_to_voxel_backward (scatter_points_cuda.cu:243-315)."""
+    feats = np.asarray(feats, np.float32)
+    g = np.zeros_like(feats)
+    keep = coors_map >= 0
+    if reduce_type in ("sum", "mean"):
+        g[keep] = grad_reduced[coors_map[keep]]
+        if reduce_type == "mean":
+            g[keep] /= count[coors_map[keep]][:, None].astype(np.float32)
+        return g
+    m, c = reduced.shape
+    frm = np.full((m, c), feats.shape[0], np.int64)          # :286 full(num_input)
+    for i in np.nonzero(keep)[0]:                           # :145-160 smallest index attaining max
+        v = coors_map[i]
+        hit = feats[i] == reduced[v]
+        frm[v, hit] = np.minimum(frm[v, hit], i)
+    for v in range(m):
+        for ch in range(c):
+            if frm[v, ch] < feats.shape[0]:
+                g[frm[v, ch], ch] = grad_reduced[v, ch]
+    return g
+
+
+# ----------------------------------------------------------------------------- depth images
+def _dot3(m, x, y, z):
+    f = np.float32
+    return f(f(f(m[0] * x) + f(m[1] * y)) + f(m[2] * z))
+
+
+def _inverse3(a):
+    """3x3 inverse by the adjugate, fp32 op by op (stands in for torch.inverse, base.py:291)."""
+    a = np.asarray(a, np.float32).reshape(9)
+    f = np.float32
+    c00 = f(f(a[4] * a[8]) - f(a[5] * a[7]))
+    c01 = f(f(a[3] * a[8]) - f(a[5] * a[6]))
+    c02 = f(f(a[3] * a[7]) - f(a[4] * a[6]))
+    det = f(f(f(a[0] * c00) - f(a[1] * c01)) + f(a[2] * c02))
+    inv = [c00 / det, f(f(a[2] * a[7]) - f(a[1] * a[8])) / det, f(f(a[1] * a[5]) - f(a[2] * a[4])) / det,
+           f(-c01) / det, f(f(a[0] * a[8]) - f(a[2] * a[6])) / det, f(f(a[2] * a[3]) - f(a[0] * a[5])) / det,
+           c02 / det, f(f(a[1] * a[6]) - f(a[0] * a[7])) / det, f(f(a[0] * a[4]) - f(a[1] * a[3])) / det]
+    return np.asarray(inv, np.float32)
+
+
+def points_to_depth(points, lidar2image, img_aug_matrix, lidar_aug_matrix, image_size,
+                    depth_input="scalar", depth_bins=None, add_depth_features=False):
+    """BaseDepthTransform.forward's depth image for ONE sample (base.py:279-329): points [N, F],
+    lidar2image / img_aug_matrix [ncam, 4, 4], lidar_aug_matrix [4, 4] -> [ncam, channels, H, W].
+    Every step is an explicit fp32 operation in the reference's order (inverse aug :290-293,
+    lidar2image :295-296, clamp + divide :298-300, image aug :303-305, on-image test :309-314,
+    .long() :316).  Colliding points: the last one (largest index) wins -- the sequential reading of
+    the index_put at :319.  Like the reference after its in-place `cur_coords -= trans` (:290), the
+    optional feature channels (:327-329) carry xyz minus the lidar-aug translation."""
+    f = np.float32
+    pts = np.asarray(points, np.float32)
+    n, nf = pts.shape
+    H, W = int(image_size[0]), int(image_size[1])
+    la = np.asarray(lidar_aug_matrix, np.float32)
+    l2i = np.asarray(lidar2image, np.float32)
+    ia = np.asarray(img_aug_matrix, np.float32)
+    ncam = l2i.shape[0]
+    one_hot = depth_input == "one-hot"
+    feat = nf if add_depth_features else 0
+    channels = (int(depth_bins) if one_hot else 1) + feat
+    depth = np.zeros((ncam, channels, H, W), np.float32)
+    inv = _inverse3(la[:3, :3])
+    with np.errstate(all="ignore"):
+        x1, y1, z1 = (pts[:, 0] - la[0, 3]).astype(f), (pts[:, 1] - la[1, 3]).astype(f), (pts[:, 2] - la[2, 3]).astype(f)
+        x2, y2, z2 = _dot3(inv[0:3], x1, y1, z1), _dot3(inv[3:6], x1, y1, z1), _dot3(inv[6:9], x1, y1, z1)
+        shifted = pts.copy()
+        shifted[:, 0], shifted[:, 1], shifted[:, 2] = x1, y1, z1
+        for cam in range(ncam):
+            L, A = l2i[cam], ia[cam]
+            x3 = f(_dot3(L[0, :3], x2, y2, z2) + L[0, 3])
+            y3 = f(_dot3(L[1, :3], x2, y2, z2) + L[1, 3])
+            z3 = f(_dot3(L[2, :3], x2, y2, z2) + L[2, 3])
+            z3 = np.minimum(np.maximum(z3, f(1e-5)), f(1e5)).astype(f)
+            x3, y3 = (x3 / z3).astype(f), (y3 / z3).astype(f)
+            u = f(_dot3(A[0, :3], x3, y3, z3) + A[0, 3])
+            v = f(_dot3(A[1, :3], x3, y3, z3) + A[1, 3])
+            on = (v < f(H)) & (v >= 0) & (u < f(W)) & (u >= 0)
+            idx = np.nonzero(on)[0]                          # ascending: later points overwrite
+            row, col = v[idx].astype(np.int64), u[idx].astype(np.int64)
+            if one_hot:
+                bins = np.minimum(z3[idx], f(depth_bins - 1)).astype(np.int64)
+                depth[cam, bins, row, col] = 1.0
+            else:
+                depth[cam, 0, row, col] = z3[idx]           # numpy fancy assignment: last write wins
+            if feat:
+                depth[cam, channels - feat:, row, col] = shifted[idx]   # result dims: (point, channel)
+    return depth
+
+
 # ------------------------------------------------------------------------------------- spconv
 def conv_output_size(input_size, kernel_size, stride, padding, dilation):
     """get_conv_output_size, mmdet3d/ops/spconv/ops.py:20-31."""

@@ -178,8 +178,51 @@ def gen_vtransform():
                         dims=np.array(captured["dims"]), x_rows=captured["x_rows"])
 
 
+def gen_depth():
+    """BaseDepthTransform.forward's LiDAR depth images (base.py:279-329) run from the REFERENCE source
+    on the CPU (single thread, so the index_put at :319 is sequential: last point wins) for a
+    2-camera rig with image + lidar augmentation: 'scalar' depth and 'one-hot' + point features."""
+    from bevfusion_b200 import synthetic as S
+    captured = {}
+    mod = load_reference_base_transform(captured)
+    cfg = S.CONFIGS["tiny"]
+
+    class Stop(Exception):
+        pass
+
+    class Probe(mod.BaseDepthTransform):
+        def get_cam_feats(self, img, depth, mats_dict):
+            captured["depth"] = depth.clone()
+            raise Stop()
+
+    torch.set_num_threads(1)
+    B = 2
+    M = S.lidar_camera_matrices(cfg["n_cam"], cfg["image_size"], B)
+    clouds = [S.lidar_cloud(seed=11 + b, sweeps=1)[::7].copy() for b in range(B)]
+    out = {}
+    for tag, kw in (("scalar", dict(depth_input="scalar", add_depth_features=False)),
+                    ("onehot_feats", dict(depth_input="one-hot", add_depth_features=True))):
+        t = Probe(in_channels=8, out_channels=cfg["C"], image_size=cfg["image_size"],
+                  feature_size=cfg["feature_size"], xbound=cfg["xbound"], ybound=cfg["ybound"],
+                  zbound=cfg["zbound"], dbound=cfg["dbound"], use_points="lidar", height_expand=False, **kw)
+        pts = [torch.from_numpy(c.copy()) for c in clouds]      # the reference shifts these in place
+        img = torch.zeros(B, cfg["n_cam"], 3, *cfg["image_size"])
+        try:
+            t(img, pts, None, M["camera2lidar"], torch.eye(4).repeat(B, 1, 1), M["lidar2camera"], M["lidar2image"],
+              M["cam_intrinsic"], M["camera2lidar"], M["img_aug_matrix"], M["lidar_aug_matrix"], None)
+        except Stop:
+            pass
+        out["depth_" + tag] = captured["depth"].numpy()
+        out["bins_" + tag] = t.D
+    np.savez_compressed(os.path.join(HERE, "depth_tiny.npz"), points0=clouds[0], points1=clouds[1],
+                        lidar2image=M["lidar2image"].numpy(), img_aug_matrix=M["img_aug_matrix"].numpy(),
+                        lidar_aug_matrix=M["lidar_aug_matrix"].numpy(),
+                        image_size=np.array(cfg["image_size"]), **out)
+
+
 if __name__ == "__main__":
     gen_vtransform()
+    gen_depth()
     gen_voxelize()
     gen_spconv()
     gen_bev_pool()

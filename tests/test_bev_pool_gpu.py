@@ -310,3 +310,31 @@ def test_plan_layout_matches_reference_path_multi_z(cuda):
     out = plan(x)
     assert tuple(out.shape) == tuple(ref.shape) == (2, 160, 64, 64)
     assert float((out - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
+
+
+def test_fuser_input_written_in_place(cuda):
+    """camera BEV (plan output) and LiDAR BEV (encoder dense output) written straight into the
+    channel slices of one [B, 80+256, X, Y] buffer == torch.cat of the separate results
+    (fusers/conv.py:16)."""
+    from bevfusion_b200 import synthetic as S
+    from bevfusion_b200.bev_pool import BEVPoolPlan
+    from bevfusion_b200.spconv import ops as sp_ops
+    cfg = dict(S.CONFIGS["tiny"]); cfg["zbound"] = (-10.0, 10.0, 10.0)
+    geom, _ = S.camera_geometry("tiny", batch=2, device=cuda)
+    x = S.lifted_features("tiny", batch=2, device=cuda, seed=3)
+    plan = BEVPoolPlan(geom, cfg["xbound"], cfg["ybound"], cfg["zbound"])
+    cam = plan(x)
+    B, CC, X, Y = cam.shape
+    rng = np.random.default_rng(0)
+    n, c, Z = 500, 8, 2
+    idx = np.unique(np.stack([rng.integers(0, B, n), rng.integers(0, X, n), rng.integers(0, Y, n),
+                              rng.integers(0, Z, n)], 1), axis=0).astype(np.int32)
+    feats = torch.from_numpy(rng.standard_normal((idx.shape[0], c)).astype(np.float32)).to(cuda)
+    indices = torch.from_numpy(idx).to(cuda)
+    lidar = sp_ops.sparse_to_dense(feats, indices, B, (X, Y, Z), z_major=True)
+    buf = torch.full((B, CC + c * Z, X, Y), float("nan"), device=cuda)
+    plan(x, out=buf[:, :CC])
+    sp_ops.sparse_to_dense(feats, indices, B, (X, Y, Z), z_major=True, out=buf[:, CC:])
+    assert torch.equal(buf, torch.cat([cam, lidar], 1))
+    with pytest.raises(ValueError):
+        plan(x, out=buf[:, :, :, 1:])

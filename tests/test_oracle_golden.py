@@ -131,3 +131,38 @@ def test_vtransform_matches_reference_source(golden_dir):
     assert np.array_equal(coords[kept], g["coords"])
     B, D, H, W = (int(v) for v in g["dims"])
     assert (B, D, H, W) == (2, int(onx[2]), int(onx[0]), int(onx[1]))
+
+
+def test_depth_images_vs_reference_source(golden_dir):
+    """oracle.points_to_depth against BaseDepthTransform.forward's depth tensor produced by the
+    reference source itself (tests/golden/make_golden.py::gen_depth): identical pixel sets, one-hot
+    bins and feature channels bit-equal, scalar distances within 1e-5 (the reference's matmul /
+    torch.inverse round differently in the last bit)."""
+    g = np.load(os.path.join(golden_dir, "depth_tiny.npz"))
+    cases = (("scalar", dict(depth_input="scalar")),
+             ("onehot_feats", dict(depth_input="one-hot", depth_bins=int(g["bins_onehot_feats"]),
+                                   add_depth_features=True)))
+    for tag, kw in cases:
+        gold = g["depth_" + tag]
+        for b in range(2):
+            d = oracle.points_to_depth(g["points%d" % b], g["lidar2image"][b], g["img_aug_matrix"][b],
+                                       g["lidar_aug_matrix"][b], g["image_size"], **kw)
+            assert d.shape == gold[b].shape
+            assert (gold[b] != 0).sum() > 500
+            assert np.array_equal(d != 0, gold[b] != 0)
+            if tag == "scalar":
+                assert np.allclose(d, gold[b], rtol=1e-5, atol=1e-5)
+            else:
+                assert np.array_equal(d, gold[b])
+
+
+def test_depth_oracle_last_point_wins():
+    """colliding points: the fancy-index assignment in the oracle must mean 'largest index wins'."""
+    eye = np.eye(4, dtype=np.float32)
+    l2i = eye[None].copy()
+    pts = np.array([[2.0, 3.0, 1.0, 0.1, 0.0], [2.2, 3.4, 1.0, 0.2, 0.0], [4.0, 1.0, 2.0, 0.3, 0.0],
+                    [2.1, 3.9, 1.0, 0.4, 0.0]], np.float32)
+    d = oracle.points_to_depth(pts, l2i, eye[None], eye, (8, 8), add_depth_features=True)
+    assert d[0, 0, 3, 2] == 1.0 and d[0, 4, 3, 2] == np.float32(0.4)     # point 3 beats 0 and 1
+    assert d[0, 0, 0, 2] == 2.0 and d[0, 4, 0, 2] == np.float32(0.3)     # (4,1)/2 -> col 2,row 0
+    assert (d[0, 0] != 0).sum() == 2

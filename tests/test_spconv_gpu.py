@@ -263,6 +263,19 @@ def test_lidar_branch_full_size(cuda):
     assert bool(torch.isfinite(out).all())
     nz = (out.abs().sum(1) > 0).float().mean()
     assert 0.05 < float(nz) < 0.9
+    # full-size parity: the same encoder run op by op through the reference's own CUDA extension
+    ref = ref_module("sparse_conv_ext_ref")
+    if ref is not None:
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            with torch.no_grad():
+                gold = reference_encoder_forward(ref, m, feats, coords, 1)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
+        assert tuple(gold.shape) == tuple(out.shape)
+        assert bool(((gold != 0) == (out != 0)).float().mean() > 0.9999)      # same active BEV cells
+        assert float((out - gold).abs().max()) <= 1e-4 * float(gold.abs().max())
 
 
 @pytest.mark.parametrize("geom", list(GEOMS))
