@@ -82,8 +82,8 @@ __device__ __forceinline__ bool project(const DepthSmem &sm, int cam, float px, 
   float x3 = __fadd_rn(dot3(L.r + 0, x2, y2, z2), L.t[0]);
   float y3 = __fadd_rn(dot3(L.r + 3, x2, y2, z2), L.t[1]);
   float z3 = __fadd_rn(dot3(L.r + 6, x2, y2, z2), L.t[2]);
+  if (!(z3 == z3)) return false;       // torch.clamp keeps NaN, which then fails the on-image test
   z3 = fminf(fmaxf(z3, 1e-5f), 1e5f);  // torch.clamp; `dist` aliases the clamped row (:298-299)
-  if (!(z3 == z3)) return false;
   x3 = __fdiv_rn(x3, z3);
   y3 = __fdiv_rn(y3, z3);
   const Mat34 &A = sm.ia[cam];
