@@ -327,6 +327,24 @@ def run_ours(args, rank, world, local_rank):
     ctx = torch.randn(1, 6, 32, 88, 80, device=device)
     lift_ms = time_us(lambda: hp.plan.lift_pool(depth, ctx))
     del og, depth, ctx
+    # SURVEY.md section 8(f) rows built after the path itself (timed alone, CUDA events, median of 20):
+    from bevfusion_b200 import synthetic as S_
+    from bevfusion_b200.scatter_points import dynamic_scatter
+    from bevfusion_b200.voxelize import voxel_layer, voxelize_mean_fused
+    from bevfusion_b200.vtransform import points_to_depth
+    L_ = S_.LIDAR_C3
+    fused_vox_ms = time_us(lambda: voxelize_mean_fused(pts, L_["voxel_size"], L_["point_cloud_range"], 10, 160000, 0))
+    unfused_vox_ms = time_us(lambda: voxelize_mean(*hp.voxelize(pts), 0))
+    dcoors = torch.zeros(pts.shape[0], 3, dtype=torch.int32, device=device)
+    voxel_layer.dynamic_voxelize(pts, dcoors, L_["voxel_size"], L_["point_cloud_range"], 3)
+    scatter_ms = time_us(lambda: dynamic_scatter(pts, dcoors, "mean"))
+    M_ = S_.lidar_camera_matrices(6, (256, 704), batch=1)
+    margs = (M_["lidar2image"].to(device), M_["img_aug_matrix"].to(device), M_["lidar_aug_matrix"].to(device), (256, 704))
+    depth_ms = time_us(lambda: points_to_depth([pts], *margs))
+    next_rows = {"voxelize_mean_fused_ms": round(fused_vox_ms, 4), "voxelize_then_mean_ms": round(unfused_vox_ms, 4),
+                 "dynamic_scatter_mean_ms": round(scatter_ms, 4), "lidar_depth_images_6x256x704_ms": round(depth_ms, 4),
+                 "points": int(pts.shape[0]),
+                 "note": "each includes its host-side result-size readback (.item()) where the API returns sized tensors"}
     pool_gbs = pool_bytes / (pool_ms * 1e-3) / 1e9
     op_gbs = pool_bytes / (op_ms * 1e-3) / 1e9
     enc_tflops = flops / (stages["encoder_ms"] * 1e-3) / 1e12
@@ -379,6 +397,7 @@ def run_ours(args, rank, world, local_rank):
                            "fused_lift_pool_ms": round(lift_ms, 4),
                            "note": "backward = bevpool_bwd_kernel through perm (660 MB algorithmic); fused lift+pool reads "
                                    "depth (8 MB) + L2-resident ctx (5.4 MB) instead of the 638 MB lifted volume"},
+        "next_rows": next_rows,
         "roofline": dominant, "roofline_bev_pool": roof_pool, "roofline_bev_pool_op": roof_pool_op,
         "roofline_encoder": roof_enc, "roofline_voxelize": roof_vox,
         "cpu_baseline": cpu, "clocks": clocks,

@@ -58,7 +58,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n\t"   // suspend, do not spin
       "@p bra WAIT_DONE;\n\t"
       "bra WAIT_LOOP;\n\t"
       "WAIT_DONE:\n\t}"
@@ -397,8 +397,7 @@ struct TcParamsV4 {
   int acc_cols;       // accumulator columns (>= 32)
   int tmem_cols;      // allocation (power of two >= acc_cols + nsa * nsplit * 32)
   long long *prof;    // optional: per-role cycle counters of CTA 0 (dev profiling)
-  int csz;            // thread-block cluster size (1, 2 or 4): the weight stages are multicast
-  int nacc;           // independent TMEM accumulators (1, 2 or 4), summed in the epilogue
+  int nmerge;         // 3xTF32 only: A_hi x [W_hi | W_lo] as ONE N = 2*c_out MMA (see the MMA issuer)
 };
 
 __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16]) {
@@ -426,6 +425,12 @@ __device__ __forceinline__ void tc_mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem,
 // instruction descriptor for kind::f16 with bf16 operands: c=F32 (bit 4), a=b=BF16 (1 at bits 7, 10)
 __host__ __device__ inline uint32_t umma_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// two fp32 -> packed bf16x2 (round to nearest even): `lo` lands in bits 0..15, `hi` in bits 16..31
+__device__ __forceinline__ uint32_t cvt_bf16x2(float hi, float lo) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
 }
 // fp32 -> bf16 (round to nearest even), bit pattern in the low 16 bits
 __device__ __forceinline__ uint32_t bf16_bits(float f) {
@@ -462,9 +467,35 @@ __device__ __forceinline__ void quad_transpose(float4 (&a)[4], int lane) {
   if (b0) { a[0] = x; a[2] = y; } else { a[1] = x; a[3] = y; }
 }
 
+// Per-role cycle counters of CTA 0 (tools/conv_prof.py) are compiled in only with
+// -DBEVB200_TC_PROFILE (BEVB200_BUILD_PROFILE=1 python bevfusion_b200/build.py): the kernel is
+// instruction-issue bound, and the clock reads alone were 3 % of its instruction stream.
+#ifdef BEVB200_TC_PROFILE
+#define TC_PROF_CLOCK(var) const long long var = clock64()
+#define TC_PROF_ADD(cond, slot, val)              \
+  do {                                            \
+    if (p.prof && (cond)) p.prof[slot] += (val);  \
+  } while (0)
+#else
+#define TC_PROF_CLOCK(var) \
+  do {                     \
+  } while (0)
+#define TC_PROF_ADD(cond, slot, val) \
+  do {                               \
+  } while (0)
+#endif
+
+// ncu on the round-1 kernel (profiles/r1_ncu_full_final.md): issue slots 62 % busy, 2900 warp
+// instructions per K block per CTA of which ~750 were the gather / split / store work itself.  The
+// rest was loop bookkeeping, which this version removes: ring stage and phase are running
+// counters (no `it % nsa`, `it / nsa` with run-time divisors: ~20 integer divisions per K block),
+// a gather address is ONE IMAD.WIDE (base + row * row_bytes), the four neighbour indices of a quad
+// come from one LDS.128 instead of a load plus four shuffles, kernel parameters are read once, the
+// waits suspend on the mbarrier (try_wait with a time hint) instead of spinning, and the cycle
+// counters are compiled out.
 template <int NSPLIT>
 __global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v4(const TcParamsV4 p) {
-  const long long kernel_t0 = clock64();
+  TC_PROF_CLOCK(kernel_t0);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -474,27 +505,27 @@ __global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v4(const TcPar
   // weight stage serves TWO 32-wide K blocks of A.
   constexpr bool BF = NSPLIT == 3;
   constexpr int NPART = BF ? 2 : NSPLIT;
-  const int b_part_bytes = p.c_out * 128;
+  const int c_out = p.c_out, nsa = p.nsa, nsb = p.nsb, n_iters = p.nkb;
+  const int b_part_bytes = c_out * 128;
   const int b_stage_bytes = NPART * b_part_bytes;
   __shared__ uint64_t bars[4 * kMaxStages + 1];
   __shared__ uint32_t tmem_base_s;
   const uint32_t a_full = smem_u32(&bars[0]), a_empty = smem_u32(&bars[kMaxStages]);
   const uint32_t b_full = smem_u32(&bars[2 * kMaxStages]), b_empty = smem_u32(&bars[3 * kMaxStages]);
   const uint32_t accbar = smem_u32(&bars[4 * kMaxStages]);
-  int32_t *nbr_s = reinterpret_cast<int32_t *>(smem + (size_t)p.nsb * b_stage_bytes);
+  int32_t *nbr_s = reinterpret_cast<int32_t *>(smem + (size_t)nsb * b_stage_bytes);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row0 = blockIdx.x * kTileM;
-  const int n_iters = p.nkb;
 
   if (tid == 0) {
-    for (int s = 0; s < p.nsa; ++s) {
+    for (int s = 0; s < nsa; ++s) {
       mbar_init(a_full + 8 * s, 8);   // one arrival per producer warp
       mbar_init(a_empty + 8 * s, 1);
     }
-    for (int s = 0; s < p.nsb; ++s) {
+    for (int s = 0; s < nsb; ++s) {
       mbar_init(b_full + 8 * s, 1);
-      mbar_init(b_empty + 8 * s, p.csz);   // released by the MMA warp of every CTA of the cluster
+      mbar_init(b_empty + 8 * s, 1);
     }
     mbar_init(accbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -506,32 +537,30 @@ __global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v4(const TcPar
   }
   tc_fence_before();
   __syncthreads();
-  if (p.csz > 1) cluster_sync_all();      // peers' barriers are initialised before any multicast
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
-  const uint16_t cmask = (uint16_t)((1u << p.csz) - 1u);
-  const uint32_t a_ring = tmem_base + (uint32_t)(p.nacc * p.acc_cols);   // column offset of A stage 0
+  const uint32_t a_ring = tmem_base + (uint32_t)p.acc_cols;            // column offset of A stage 0
   constexpr uint32_t kAStageCols = BF ? 32u : (uint32_t)NSPLIT * 32u;   // BF16: 16 cols hi | 16 cols lo
 
   if (warp < 8) {
     // =============================== producers ===========================================
     // TMEM lane quarter q = warp & 3 is the only one this warp may touch: row = 32 q + lane
     const int q = warp & 3, half = warp >> 2;
-    const int r = q * 32 + lane;
     {
       // neighbour table of the tile: all (<= 14) loads of a thread are issued before any is used
       constexpr int kPer = (27 * kTileM + kTcProducerThreads - 1) / kTcProducerThreads;
+      const int n_tab = p.kvol * kTileM, n_out = p.n_out, n_in = p.n_in;
       int tv[kPer];
 #pragma unroll
       for (int u = 0; u < kPer; ++u) {
         const int i = tid + u * kTcProducerThreads;
         const int k = i >> 7, rr = i & 127, o = row0 + rr;
-        tv[u] = (i < p.kvol * kTileM && o < p.n_out) ? __ldg(p.nbr + (long long)k * p.n_out + o) : -1;
+        tv[u] = (i < n_tab && o < n_out) ? __ldg(p.nbr + (long long)k * n_out + o) : -1;
       }
 #pragma unroll
       for (int u = 0; u < kPer; ++u) {
         const int i = tid + u * kTcProducerThreads;
-        if (i < p.kvol * kTileM) nbr_s[i] = tv[u] >= p.n_in ? -1 : tv[u];
+        if (i < n_tab) nbr_s[i] = tv[u] >= n_in ? -1 : tv[u];
       }
     }
     asm volatile("bar.sync 1, %0;" ::"n"(kTcProducerThreads) : "memory");
@@ -540,104 +569,110 @@ __global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v4(const TcPar
     // quarter, 4 lanes x 16 B per row (64 contiguous bytes), so a warp-level LDG.128 touches 8
     // cache lines instead of 32 (measured: the one-row-per-lane mapping was L1 wavefront bound).
     // The quad transpose at consume time hands every lane the 64 bytes of ITS row.
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const uint32_t row_bytes = (uint32_t)p.c_in * 4u;
+    const char *fbase = reinterpret_cast<const char *>(p.features) + 16 * (lane & 3);
+    const int32_t *nb_quad = nbr_s + q * 32 + (lane & ~3);   // the 4 rows of this lane's quad: one int4
+    const int cin_shift = p.cin_shift, cin_mask = p.c_in - 1, kvol = p.kvol;
     auto issue = [&](int it, float4 (&v)[4]) {
       const int kk = it * kKBlock + half * 16;
-      const int k = kk >> p.cin_shift;
-      const int ch = (kk & (p.c_in - 1)) + 4 * (lane & 3);
-      const int src_own = k < p.kvol ? nbr_s[k * kTileM + r] : -1;
+      const int k = kk >> cin_shift;
+      const char *base = fbase + ((kk & cin_mask) << 2);
+      int4 s4 = make_int4(-1, -1, -1, -1);
+      if (k < kvol) s4 = *reinterpret_cast<const int4 *>(nb_quad + k * kTileM);
+      const int src[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int src = __shfl_sync(0xffffffffu, src_own, (lane & ~3) + t);
-        v[t] = src >= 0 ? __ldg(reinterpret_cast<const float4 *>(p.features + (long long)src * p.c_in + ch))
-                        : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+      for (int t = 0; t < 4; ++t)
+        v[t] = src[t] >= 0 ? __ldg(reinterpret_cast<const float4 *>(
+                                 base + (unsigned long long)(uint32_t)src[t] * row_bytes))
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
     };
     constexpr int PD = 3;   // K blocks prefetched in registers (4 spills under the 2-CTA/SM register cap)
     float4 v[PD][4];
 #pragma unroll
     for (int j = 0; j < PD; ++j)
       if (j < n_iters) issue(j, v[j]);
-    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    int s = 0;              // A ring stage and its phase, advanced once per K block
+    uint32_t ph = 0;
+    const uint32_t col0 = a_ring + (uint32_t)(half * (BF ? 8 : 16));
     for (int it0 = 0; it0 < n_iters; it0 += PD) {
 #pragma unroll
       for (int jj = 0; jj < PD; ++jj) {
         const int it = it0 + jj;
         if (it < n_iters) {
-          const int s = it % p.nsa;
-          const uint32_t ph = (uint32_t)(it / p.nsa) & 1u;
-          const long long t0 = clock64();
+          TC_PROF_CLOCK(t0);
           quad_transpose(v[jj], lane);
-          if (lane == 0) mbar_wait(a_empty + 8 * s, ph ^ 1u);   // one poller per warp
+          if (lane == 0) mbar_wait(a_empty + 8 * s, ph ^ 1u);   // one waiter per warp
           __syncwarp();
           tc_fence_after();
-          const long long t1 = clock64();
+          TC_PROF_CLOCK(t1);
+          const uint32_t col = lane_base + col0 + (uint32_t)s * kAStageCols;
           if constexpr (BF) {
             // 16 K values of this row -> 8 packed bf16 words hi + 8 words lo (k even in the low half)
             uint32_t hi[8], lo[8];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const float f[4] = {v[jj][j].x, v[jj][j].y, v[jj][j].z, v[jj][j].w};
-              uint32_t h[4], l[4];
+#pragma unroll
+              for (int e = 0; e < 4; e += 2) {
+                const uint32_t h = cvt_bf16x2(f[e + 1], f[e]);
+                const float h0 = __uint_as_float(h << 16), h1 = __uint_as_float(h & 0xffff0000u);
+                hi[2 * j + e / 2] = h;
+                lo[2 * j + e / 2] = cvt_bf16x2(f[e + 1] - h1, f[e] - h0);
+              }
+            }
+            tc_st8(col, hi);
+            tc_st8(col + 16u, lo);
+          } else {
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float f[4] = {v[jj][j].x, v[jj][j].y, v[jj][j].z, v[jj][j].w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                h[e] = bf16_bits(f[e]);
-                l[e] = bf16_bits(f[e] - __uint_as_float(h[e] << 16));
+                hi[4 * j + e] = __float_as_uint(f[e]) & 0xffffe000u;
+                lo[4 * j + e] = __float_as_uint(f[e] - __uint_as_float(hi[4 * j + e]));
               }
-              hi[2 * j] = h[0] | (h[1] << 16); hi[2 * j + 1] = h[2] | (h[3] << 16);
-              lo[2 * j] = l[0] | (l[1] << 16); lo[2 * j + 1] = l[2] | (l[3] << 16);
             }
-            const uint32_t col = a_ring + (uint32_t)s * kAStageCols + (uint32_t)(half * 8);
-            tc_st8(lane_base + col, hi);
-            tc_st8(lane_base + col + 16u, lo);
-          } else {
-          uint32_t hi[16], lo[16];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float f[4] = {v[jj][j].x, v[jj][j].y, v[jj][j].z, v[jj][j].w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              hi[4 * j + e] = __float_as_uint(f[e]) & 0xffffe000u;
-              lo[4 * j + e] = __float_as_uint(f[e] - __uint_as_float(hi[4 * j + e]));
-            }
-          }
-          const uint32_t col = a_ring + (uint32_t)s * kAStageCols + (uint32_t)(half * 16);
-          tc_st16(lane_base + col, hi);
-          if (NSPLIT == 2) tc_st16(lane_base + col + 32u, lo);
+            tc_st16(col, hi);
+            if (NSPLIT == 2) tc_st16(col + 32u, lo);
           }
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(a_full + 8 * s);            // 8 arrivals per K block, not 256
-          const long long t2 = clock64();
+          if (++s == nsa) { s = 0; ph ^= 1u; }
+          TC_PROF_CLOCK(t2);
           if (it + PD < n_iters) issue(it + PD, v[jj]);
-          if (p.prof && blockIdx.x == 0 && tid == 0) {
-            p.prof[0] += t1 - t0;             // transpose + wait for a free TMEM stage
-            p.prof[1] += t2 - t1;             // split + tcgen05.st + wait::st + arrive
-            p.prof[2] += clock64() - t2;      // issue of the next gather loads
-          }
+          TC_PROF_ADD(blockIdx.x == 0 && tid == 0, 0, t1 - t0);             // transpose + wait for a free stage
+          TC_PROF_ADD(blockIdx.x == 0 && tid == 0, 1, t2 - t1);             // split + tcgen05.st + arrive
+          TC_PROF_ADD(blockIdx.x == 0 && tid == 0, 2, clock64() - t2);      // issue of the next gather loads
         }
       }
     }
     // =============================== epilogue ============================================
-    const long long e0 = clock64();
+    TC_PROF_CLOCK(e0);
     mbar_wait(accbar, 0);
     tc_fence_after();
-    if (p.prof && blockIdx.x == 0 && tid == 0) p.prof[3] += clock64() - e0;   // drain: last MMAs
+    TC_PROF_ADD(blockIdx.x == 0 && tid == 0, 3, clock64() - e0);   // drain: last MMAs
     const int orow = row0 + q * 32 + lane;
-    const int ncol_half = p.c_out / 2;
+    const int ncol_half = c_out / 2;
     const int col_begin = half * ncol_half;
+    const bool row_ok = orow < p.n_out;
+    const float *scale = p.scale, *shift = p.shift;
+    const int relu = p.relu;
     for (int c0 = col_begin; c0 < col_begin + ncol_half; c0 += 16) {
       float acc[16];
       tc_ld16(tmem_base + lane_base + (uint32_t)c0, acc);
-      for (int ai = 1; ai < p.nacc; ++ai) {
+      if (p.nmerge) {   // columns [c_out, 2 c_out) hold the hi x lo partial sums
         float more[16];
-        tc_ld16(tmem_base + lane_base + (uint32_t)(ai * p.acc_cols + c0), more);
+        tc_ld16(tmem_base + lane_base + (uint32_t)(c_out + c0), more);
 #pragma unroll
         for (int e = 0; e < 16; ++e) acc[e] += more[e];
       }
-      if (orow < p.n_out) {
-        float *dst = p.out + (long long)orow * p.c_out + c0;
-        const float *res = p.residual ? p.residual + (long long)orow * p.c_out + c0 : nullptr;
+      if (row_ok) {
+        float *dst = p.out + (long long)orow * c_out + c0;
+        const float *res = p.residual ? p.residual + (long long)orow * c_out + c0 : nullptr;
         const int ncols = min(16, col_begin + ncol_half - c0);
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
@@ -646,15 +681,15 @@ __global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v4(const TcPar
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               float t = acc[j + e];
-              if (p.scale) t *= __ldg(p.scale + c0 + j + e);
-              if (p.shift) t += __ldg(p.shift + c0 + j + e);
+              if (scale) t *= __ldg(scale + c0 + j + e);
+              if (shift) t += __ldg(shift + c0 + j + e);
               y[e] = t;
             }
             if (res) {
               const float4 rv = __ldg(reinterpret_cast<const float4 *>(res + j));
               y[0] += rv.x; y[1] += rv.y; y[2] += rv.z; y[3] += rv.w;
             }
-            if (p.relu) {
+            if (relu) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) y[e] = fmaxf(y[e], 0.f);
             }
@@ -665,17 +700,23 @@ __global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v4(const TcPar
     }
   } else if (warp == 8) {
     // =============================== MMA issuer ==========================================
-    const uint32_t idesc = BF ? umma_idesc_bf16(kTileM, p.c_out) : umma_idesc_tf32(kTileM, p.c_out);
+    const uint32_t idesc = BF ? umma_idesc_bf16(kTileM, c_out) : umma_idesc_tf32(kTileM, c_out);
+    const uint32_t idesc2 = BF ? umma_idesc_bf16(kTileM, 2 * c_out)   // merged [W_hi | W_lo] operand
+                               : umma_idesc_tf32(kTileM, 2 * c_out);
+    const int nmerge = p.nmerge;
+    int sa = 0, sb = 0;
+    uint32_t pa = 0, pb = 0;
     for (int it = 0; it < n_iters; ++it) {
-      const int gb = BF ? (it >> 1) : it;          // weight stage index (64 K values per stage in BF16)
-      const int sa = it % p.nsa, sb = gb % p.nsb;
-      const long long m0 = clock64();
-      mbar_wait(a_full + 8 * sa, (uint32_t)(it / p.nsa) & 1u);
-      const long long m1 = clock64();
-      mbar_wait(b_full + 8 * sb, (uint32_t)(gb / p.nsb) & 1u);
+      TC_PROF_CLOCK(m0);
+      mbar_wait(a_full + 8 * sa, pa);
+      TC_PROF_CLOCK(m1);
+      mbar_wait(b_full + 8 * sb, pb);   // BF16: already complete for the second K block of a stage
       tc_fence_after();
-      const long long m2 = clock64();
-      if (p.prof && blockIdx.x == 0 && lane == 0) { p.prof[4] += m1 - m0; p.prof[5] += m2 - m1; }
+      TC_PROF_CLOCK(m2);
+      TC_PROF_ADD(blockIdx.x == 0 && lane == 0, 4, m1 - m0);
+      TC_PROF_ADD(blockIdx.x == 0 && lane == 0, 5, m2 - m1);
+      const bool last = it == n_iters - 1;
+      const bool b_done = !BF || (it & 1) || last;   // the weight stage is free after its last K block
       if (elect_one_sync()) {
         const uint32_t a_hi = a_ring + (uint32_t)sa * kAStageCols;   // lane 0, column offset
         const uint32_t a_lo = a_hi + (BF ? 16u : 32u);
@@ -688,13 +729,21 @@ __global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v4(const TcPar
           // +32 B along K inside the 128-byte swizzled weight row (BF16: odd K blocks use its 2nd half)
           const uint64_t badv = (uint64_t)(ks * 2 + (BF ? (it & 1) * 4 : 0));
           const uint32_t aadv = (uint32_t)(ks * 8);   // 8 TMEM columns per K step (8 tf32 / 16 bf16)
-          // consecutive MMAs into ONE accumulator serialise at ~64 clk each whatever N is
-          // (measured: 12 MMAs = ~780 clk for N = 16 .. 64); K step ks therefore accumulates into
-          // accumulator ks % nacc, the chains overlap in the tensor pipe, the epilogue adds them
-          const int ai = ks & (p.nacc - 1);
-          const uint32_t d = tmem_base + (uint32_t)(ai * p.acc_cols);
-          const uint32_t first = (it == 0 && ks < p.nacc) ? 0u : 1u;
-          if constexpr (BF) {
+          const uint32_t d = tmem_base;
+          const uint32_t first = (it == 0 && ks == 0) ? 0u : 1u;
+          if (nmerge) {
+            // The hi and lo weight images are adjacent in the stage (same swizzle atoms), so one
+            // descriptor with N = 2*c_out multiplies A_hi by both: columns [0, c_out) collect
+            // hi*hi (+ lo*hi below), columns [c_out, 2 c_out) collect hi*lo.  2 MMAs, not 3; the
+            // epilogue adds the two column groups.
+            if constexpr (BF) {
+              tc_mma_bf16_ts(d, a_hi + aadv, b_hi + badv, idesc2, first);
+              tc_mma_bf16_ts(d, a_lo + aadv, b_hi + badv, idesc, 1u);
+            } else {
+              tc_mma_tf32_ts(d, a_hi + aadv, b_hi + badv, idesc2, first);
+              tc_mma_tf32_ts(d, a_lo + aadv, b_hi + badv, idesc, 1u);
+            }
+          } else if constexpr (BF) {
             tc_mma_bf16_ts(d, a_lo + aadv, b_hi + badv, idesc, first);
             tc_mma_bf16_ts(d, a_hi + aadv, b_lo + badv, idesc, 1u);
             tc_mma_bf16_ts(d, a_hi + aadv, b_hi + badv, idesc, 1u);
@@ -707,40 +756,35 @@ __global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v4(const TcPar
           }
         }
         tc_commit(a_empty + 8 * sa);
-        if (!BF || (it & 1) || it == n_iters - 1) {   // the weight stage is free after its last K block
-          if (p.csz > 1) tc_commit_mcast(b_empty + 8 * sb, cmask); else tc_commit(b_empty + 8 * sb);
-        }
-        if (it == n_iters - 1) tc_commit(accbar);
-        if (p.prof && blockIdx.x == 0) p.prof[6] += clock64() - m2;   // MMA issue + commits
+        if (b_done) tc_commit(b_empty + 8 * sb);
+        if (last) tc_commit(accbar);
+        TC_PROF_ADD(blockIdx.x == 0, 6, clock64() - m2);   // MMA issue + commits
       }
       __syncwarp();
+      if (++sa == nsa) { sa = 0; pa ^= 1u; }
+      if (b_done && ++sb == nsb) { sb = 0; pb ^= 1u; }
     }
   } else {
     // =============================== weight loader =======================================
-    // With a cluster, CTA rank c fetches slice c of every weight stage from L2 ONCE and multicasts
-    // it into the same ring slot of all CTAs of the cluster (their b_full barriers count the bytes);
-    // a slot is rewritten only after the MMA warps of ALL cluster CTAs released it (b_empty).
     if (lane == 0) {
-      const uint32_t crank = p.csz > 1 ? cluster_ctarank() : 0u;
-      const uint32_t slice = (uint32_t)b_stage_bytes / (uint32_t)p.csz;
       const int n_bstages = BF ? (n_iters + 1) / 2 : n_iters;
+      const char *src = reinterpret_cast<const char *>(p.wpacked);
+      int sb = 0;
+      uint32_t pb = 1;   // an untouched stage counts as released
       for (int it = 0; it < n_bstages; ++it) {
-        const int sb = it % p.nsb;
-        mbar_wait(b_empty + 8 * sb, ((uint32_t)(it / p.nsb) & 1u) ^ 1u);
+        mbar_wait(b_empty + 8 * sb, pb);
         mbar_arrive_expect_tx(b_full + 8 * sb, (uint32_t)b_stage_bytes);
-        const uint32_t dst = smem_base + (uint32_t)sb * (uint32_t)b_stage_bytes + crank * slice;
-        const char *src = reinterpret_cast<const char *>(p.wpacked) +
-                          (long long)it * (long long)b_stage_bytes + crank * slice;
-        if (p.csz > 1) bulk_copy_g2s_mcast(dst, src, slice, b_full + 8 * sb, cmask);
-        else bulk_copy_g2s(dst, src, slice, b_full + 8 * sb);
+        bulk_copy_g2s(smem_base + (uint32_t)sb * (uint32_t)b_stage_bytes, src, (uint32_t)b_stage_bytes,
+                      b_full + 8 * sb);
+        src += b_stage_bytes;
+        if (++sb == nsb) { sb = 0; pb ^= 1u; }
       }
     }
     __syncwarp();
   }
   tc_fence_before();
   __syncthreads();
-  if (p.csz > 1) cluster_sync_all();      // nobody leaves while a peer may still signal it
-  if (p.prof && blockIdx.x == 0 && tid == 0) p.prof[7] += clock64() - kernel_t0;   // whole CTA
+  TC_PROF_ADD(blockIdx.x == 0 && tid == 0, 7, clock64() - kernel_t0);   // whole CTA
   if (warp == 8) {
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
@@ -878,7 +922,13 @@ int spconv_forward_tc(const float *features, const float *weight, const float *p
     p4.features = features; p4.nbr = nbr; p4.scale = scale; p4.shift = shift; p4.residual = residual;
     p4.out = out; p4.n_in = n_in; p4.n_out = n_out; p4.c_in = c_in; p4.c_out = c_out; p4.kvol = kvol;
     p4.relu = relu; p4.nkb = nkb; p4.cin_shift = cin_shift; p4.wpacked = wpacked;
-    p4.acc_cols = acc_cols;
+    static int merge_env = -1;
+    if (merge_env < 0) {
+      const char *e = getenv("BEVB200_SPCONV_NMERGE");
+      merge_env = e ? atoi(e) : 1;
+    }
+    p4.nmerge = (merge_env && (nsplit == 2 || bf) && c_out <= 64) ? 1 : 0;
+    p4.acc_cols = p4.nmerge ? (2 * c_out < 32 ? 32 : 2 * c_out) : acc_cols;
     {
       // dev profiling: BEVB200_TC_PROF=<device pointer of 8 int64 counters, hex>
       static long long *prof_ptr = (long long *)-1;
@@ -888,19 +938,9 @@ int spconv_forward_tc(const float *features, const float *weight, const float *p
       }
       p4.prof = prof_ptr;
     }
-    // 256 TMEM columns per CTA (two CTAs per SM): nacc accumulators + A ring (>= 2 stages)
-    static int forced_nacc = -1;
-    if (forced_nacc < 0) {
-      const char *e = getenv("BEVB200_SPCONV_NACC");
-      forced_nacc = e ? atoi(e) : 0;
-    }
-    int nacc = forced_nacc ? forced_nacc : (c_out <= 32 ? 4 : (c_out <= 64 ? 2 : 1));
+    // 256 TMEM columns per CTA (two CTAs per SM): accumulator + A ring (>= 2 stages)
     const int a_stage_cols = bf ? 32 : nsplit * 32;
-    if (bf && nacc > 2) nacc = 2;                 // BF16 mode has 2 K steps per K block
-    while (nacc > 1 && nacc * p4.acc_cols + 2 * a_stage_cols > 256) nacc >>= 1;
-    if (nacc != 1 && nacc != 2 && nacc != 4) nacc = 1;
-    p4.nacc = nacc;
-    p4.nsa = (256 - nacc * p4.acc_cols) / a_stage_cols;
+    p4.nsa = (256 - p4.acc_cols) / a_stage_cols;
     if (p4.nsa > 4) p4.nsa = 4;
     p4.tmem_cols = 256;
     const int b_stage4 = (bf ? 2 : nsplit) * c_out * 128;
@@ -909,43 +949,15 @@ int spconv_forward_tc(const float *features, const float *weight, const float *p
     if (nsb4 < 2) nsb4 = 2;
     p4.nsb = nsb4;
     const size_t smem4 = (size_t)nsb4 * b_stage4 + nbr_bytes + 1024;
-    // thread-block clusters multicast the weight stages (halves the L2 reads of the weights);
-    // measured: no gain on B200 for this kernel (the limit is per-SM ingest), so off by default
-    static int forced_csz = -1;
-    if (forced_csz < 0) {
-      const char *e = getenv("BEVB200_SPCONV_CLUSTER");
-      forced_csz = e ? atoi(e) : 0;
-    }
-    int csz = forced_csz ? forced_csz : 1;
-    if (csz != 1 && csz != 2 && csz != 4) csz = 1;
-    p4.csz = csz;
-    const int grid4 = (grid_tiles + csz - 1) / csz * csz;
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(grid4);
-    cfg.blockDim = dim3(kV4Threads);
-    cfg.dynamicSmemBytes = smem4;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = csz;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    if (bf) {
-      BEVB200_CUDA(cudaFuncSetAttribute(spconv_tc_kernel_v4<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem4));
-      BEVB200_CUDA(cudaLaunchKernelEx(&cfg, spconv_tc_kernel_v4<3>, p4));
-    } else if (nsplit == 2) {
-      BEVB200_CUDA(cudaFuncSetAttribute(spconv_tc_kernel_v4<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem4));
-      BEVB200_CUDA(cudaLaunchKernelEx(&cfg, spconv_tc_kernel_v4<2>, p4));
-    } else {
-      BEVB200_CUDA(cudaFuncSetAttribute(spconv_tc_kernel_v4<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem4));
-      BEVB200_CUDA(cudaLaunchKernelEx(&cfg, spconv_tc_kernel_v4<1>, p4));
-    }
+    auto launch = [&](auto kernel) -> int {
+      BEVB200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+      kernel<<<grid_tiles, kV4Threads, smem4, st>>>(p4);
+      BEVB200_CUDA(cudaGetLastError());
+      return BEVB200_OK;
+    };
+    const int lrc = bf ? launch(spconv_tc_kernel_v4<3>)
+                       : (nsplit == 2 ? launch(spconv_tc_kernel_v4<2>) : launch(spconv_tc_kernel_v4<1>));
+    if (lrc) return lrc;
     ++g_launch_count;
   } else {
     TcParamsV2 p2;

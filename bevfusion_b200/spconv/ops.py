@@ -22,8 +22,11 @@ _PREC_NAMES = {"fp32": PREC_FP32, "tf32x3": PREC_TF32X3, "tf32": PREC_TF32, "bf1
 
 
 def default_precision():
-    """Precision of the sparse-conv GEMMs: env BEVB200_SPCONV_PRECISION in {fp32, tf32x3, tf32}."""
-    return _PREC_NAMES[os.environ.get("BEVB200_SPCONV_PRECISION", "tf32x3").lower()]
+    """Precision of the sparse-conv GEMMs: env BEVB200_SPCONV_PRECISION in {fp32, tf32x3, tf32,
+    bf16x3}.  Default bf16x3: features and weights split into two bf16 parts, three kind::f16 MMAs
+    with fp32 accumulation -- 5e-6 .. 8e-6 of max|out| against the float64 oracle (3xTF32: 1e-6 ..
+    1e-5), half the operand bytes and half the MMA instructions of 3xTF32."""
+    return _PREC_NAMES[os.environ.get("BEVB200_SPCONV_PRECISION", "bf16x3").lower()]
 
 
 def get_conv_output_size(input_size, kernel_size, stride, padding, dilation):

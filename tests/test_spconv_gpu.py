@@ -103,7 +103,7 @@ def test_conv_vs_oracle(cuda, geom, cin, cout):
     rb, out_shape = ops.get_rulebook(torch.from_numpy(idx).to(cuda), B, shape, ks, st, pd, 1, 0, subm)
     assert out_shape == gshape and rb.n_out == gids.shape[0]
     assert np.array_equal(rb.outids.cpu().numpy(), gids)              # bit-exact outputs + order
-    modes = [0] + ([1] if tc_available(cuda) else [])
+    modes = [0] + ([1, 3] if tc_available(cuda) else [])
     for prec in modes:
         out = ops.sparse_conv(torch.from_numpy(feat).to(cuda), torch.from_numpy(W).to(cuda), rb.nbr,
                               rb.n_out, precision=prec).cpu().numpy()
@@ -241,8 +241,9 @@ def test_encoder_fused_vs_modular_vs_reference(cuda):
         assert float((fused - gold).abs().max()) <= 1e-4 * float(gold.abs().max())
     if tc_available(cuda):
         with torch.no_grad():
-            tc = m(feats, coors, B, fused=True, precision=1)
-        assert float((tc - modular).abs().max()) <= 1e-4 * scale
+            for prec in (1, 3):                                      # 3xTF32 and BF16x3 (default)
+                tc = m(feats, coors, B, fused=True, precision=prec)
+                assert float((tc - modular).abs().max()) <= 1e-4 * scale
 
 
 def test_lidar_branch_full_size(cuda):
@@ -296,7 +297,7 @@ def test_backward_vs_oracle(cuda, geom, cin, cout):
     rb, _ = ops.get_rulebook(torch.from_numpy(idx).to(cuda), B, shape, ks, st, pd, 1, 0, subm)
     assert np.array_equal(rb.outids.cpu().numpy(), outids[order])
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
-    for prec in [0] + ([1] if tc_available(cuda) else []):
+    for prec in [0] + ([1, 3] if tc_available(cuda) else []):
         din, dw = ops.sparse_conv_backward(t(feat), t(W), t(g[order]), rb.nbr, precision=prec)
         assert rel_err(din.cpu().numpy(), gdin) <= 1e-4, "input grad, precision %d" % prec
         assert rel_err(dw.cpu().numpy(), gdw) <= 1e-4, "weight grad, precision %d" % prec
