@@ -397,7 +397,9 @@ struct TcParamsV4 {
   int acc_cols;       // accumulator columns (>= 32)
   int tmem_cols;      // allocation (power of two >= acc_cols + nsa * nsplit * 32)
   long long *prof;    // optional: per-role cycle counters of CTA 0 (dev profiling)
-  int nmerge;         // 3xTF32 only: A_hi x [W_hi | W_lo] as ONE N = 2*c_out MMA (see the MMA issuer)
+  int nmerge;         // A_hi x [W_hi | W_lo] as ONE N = 2*c_out MMA (see the MMA issuer)
+  int nsg;            // v5: gather staging slots per row quarter (2..4, 4 KB each)
+  int nbr_bytes;      // v5: bytes of the neighbour table in shared memory (multiple of 128)
 };
 
 __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16]) {
@@ -792,6 +794,344 @@ __global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v4(const TcPar
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// v5: the gather goes through shared memory with cp.async, in WHOLE 128-byte lines.
+//
+// What bounded v4 after its instruction stream was trimmed: (1) a warp-level LDG is processed by
+// the L1 one 128-byte line at a time, ~2 clk per line whatever part of the line is used; v4's
+// 4-lanes-per-row loads touch 8 lines per instruction for 64 B each, 256 line-visits per K block per
+// CTA, ~530 clk with two CTAs sharing the SM's L1; (2) the 4x4 register transposes (16 SHFL + as
+// many selects per 16 floats) that turn "4 lanes per row" into "lane = row" for tcgen05.st.
+// v5 splits the producers into four GATHER warps and four CONVERT warps (one of each per TMEM lane
+// quarter):
+//   gather   lane (m, c) = (lane >> 3, lane & 7) copies the 16-byte chunk c of rows 8m+t, t = 0..7,
+//            of its quarter's 32 rows with cp.async.cg (LDGSTS, 16 B, src-size 0 = zero fill for
+//            missing neighbours): one instruction = 4 rows x 128 B = 4 whole lines, 128 line-visits
+//            per K block per CTA.  The chunk lands at row*128 + ((c ^ (row & 7)) << 4) of a 4 KB
+//            staging slot (XOR swizzle: writes and reads are both bank-conflict free);
+//            cp.async.mbarrier.arrive.noinc signals the slot's `full` barrier when the bytes landed.
+//   convert  lane = row: 8 LDS.128 fetch the row's 32 floats (the transpose is free: it is just the
+//            shared-memory addressing), the slot is released, the floats are split hi/lo and
+//            written to the TMEM A stage with tcgen05.st; arrive on a_full.
+// No data registers are held across the global-load latency (the slots are the prefetch buffer),
+// there is no shuffle, and each role's loop is ~55 / ~135 instructions per K block.
+// MMA issuer, weight loader and epilogue are v4's.
+// ---------------------------------------------------------------------------------------
+constexpr int kStageSlotBytes = 32 * 128;   // one quarter's rows of one K block
+constexpr int kMaxGatherSlots = 4;
+
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst_smem, const void *src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
+template <int NSPLIT>
+__global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v5(const TcParamsV4 p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
+  constexpr bool BF = NSPLIT == 3;
+  constexpr int NPART = BF ? 2 : NSPLIT;
+  const int c_out = p.c_out, nsa = p.nsa, nsb = p.nsb, nsg = p.nsg, n_iters = p.nkb;
+  const int b_part_bytes = c_out * 128;
+  const int b_stage_bytes = NPART * b_part_bytes;
+  __shared__ uint64_t bars[4 * kMaxStages + 1 + 8 * kMaxGatherSlots];
+  __shared__ uint32_t tmem_base_s;
+  const uint32_t a_full = smem_u32(&bars[0]), a_empty = smem_u32(&bars[kMaxStages]);
+  const uint32_t b_full = smem_u32(&bars[2 * kMaxStages]), b_empty = smem_u32(&bars[3 * kMaxStages]);
+  const uint32_t accbar = smem_u32(&bars[4 * kMaxStages]);
+  const uint32_t g_full = smem_u32(&bars[4 * kMaxStages + 1]);                          // [quarter][slot]
+  const uint32_t g_empty = smem_u32(&bars[4 * kMaxStages + 1 + 4 * kMaxGatherSlots]);
+  const uint32_t ring_bytes = (uint32_t)nsb * (uint32_t)b_stage_bytes;
+  int32_t *nbr_s = reinterpret_cast<int32_t *>(smem + ring_bytes);
+  const uint32_t slots_base = smem_base + ring_bytes + (uint32_t)p.nbr_bytes;   // 128-byte aligned
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row0 = blockIdx.x * kTileM;
+
+  if (tid == 0) {
+    for (int s = 0; s < nsa; ++s) {
+      mbar_init(a_full + 8 * s, 4);   // one arrival per convert warp
+      mbar_init(a_empty + 8 * s, 1);
+    }
+    for (int s = 0; s < nsb; ++s) {
+      mbar_init(b_full + 8 * s, 1);
+      mbar_init(b_empty + 8 * s, 1);
+    }
+    for (int s = 0; s < 4 * kMaxGatherSlots; ++s) {
+      mbar_init(g_full + 8 * s, 32);   // every lane of the gather warp: cp.async arrive (noinc)
+      mbar_init(g_empty + 8 * s, 1);
+    }
+    mbar_init(accbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t a_ring = tmem_base + (uint32_t)p.acc_cols;            // column offset of A stage 0
+  constexpr uint32_t kAStageCols = BF ? 32u : (uint32_t)NSPLIT * 32u;   // BF16: 16 cols hi | 16 cols lo
+
+  if (warp < 8) {
+    const int q = warp & 3;                      // TMEM lane quarter == row quarter of the tile
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    {
+      // neighbour table of the tile: all (<= 14) loads of a thread are issued before any is used
+      constexpr int kPer = (27 * kTileM + kTcProducerThreads - 1) / kTcProducerThreads;
+      const int n_tab = p.kvol * kTileM, n_out = p.n_out, n_in = p.n_in;
+      int tv[kPer];
+#pragma unroll
+      for (int u = 0; u < kPer; ++u) {
+        const int i = tid + u * kTcProducerThreads;
+        const int k = i >> 7, rr = i & 127, o = row0 + rr;
+        tv[u] = (i < n_tab && o < n_out) ? __ldg(p.nbr + (long long)k * n_out + o) : -1;
+      }
+#pragma unroll
+      for (int u = 0; u < kPer; ++u) {
+        const int i = tid + u * kTcProducerThreads;
+        if (i < n_tab) nbr_s[i] = tv[u] >= n_in ? -1 : tv[u];
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kTcProducerThreads) : "memory");
+    const uint32_t my_slots = slots_base + (uint32_t)(q * nsg) * (uint32_t)kStageSlotBytes;
+    const uint32_t my_full = g_full + 8u * (uint32_t)(q * kMaxGatherSlots);
+    const uint32_t my_empty = g_empty + 8u * (uint32_t)(q * kMaxGatherSlots);
+
+    if (warp < 4) {
+      // =============================== gather ==============================================
+      const int m = lane >> 3, c = lane & 7;
+      const uint32_t row_bytes = (uint32_t)p.c_in * 4u;
+      const char *features = reinterpret_cast<const char *>(p.features);
+      const int32_t *nb_oct = nbr_s + q * 32 + 8 * m;      // the 8 rows of this lane's octet: two int4
+      const int cin_shift = p.cin_shift, cin_mask = p.c_in - 1, kvol = p.kvol;
+      uint32_t dst_off[8];                                  // row (8m + t), swizzled chunk c ^ t
+#pragma unroll
+      for (int t = 0; t < 8; ++t) dst_off[t] = (uint32_t)((8 * m + t) * 128 + ((c ^ t) << 4));
+      int sg = 0;
+      uint32_t pg = 0;
+      for (int it = 0; it < n_iters; ++it) {
+        const int kk = it * kKBlock + 4 * c;               // first K index of this lane's chunk
+        const int k = kk >> cin_shift;
+        const char *base = features + ((kk & cin_mask) << 2);
+        int4 i0 = make_int4(-1, -1, -1, -1), i1 = i0;
+        if (k < kvol) {
+          i0 = *reinterpret_cast<const int4 *>(nb_oct + k * kTileM);
+          i1 = *reinterpret_cast<const int4 *>(nb_oct + k * kTileM + 4);
+        }
+        const int src[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+        mbar_wait(my_empty + 8 * sg, pg ^ 1u);             // slot released by the convert warp
+        const uint32_t slot = my_slots + (uint32_t)sg * (uint32_t)kStageSlotBytes;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const bool ok = src[t] >= 0;
+          cp_async16_zfill(slot + dst_off[t], base + (unsigned long long)(uint32_t)(ok ? src[t] : 0) * row_bytes,
+                           ok ? 16u : 0u);
+        }
+        cp_async_mbar_arrive_noinc(my_full + 8 * sg);
+        if (++sg == nsg) { sg = 0; pg ^= 1u; }
+      }
+    } else {
+      // =============================== convert =============================================
+      uint32_t src_off[8];                                  // row = lane, chunk j at j ^ (lane & 7)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) src_off[j] = (uint32_t)(lane * 128 + ((j ^ (lane & 7)) << 4));
+      int sg = 0, sa = 0;
+      uint32_t pg = 0, pa = 0;
+      for (int it = 0; it < n_iters; ++it) {
+        mbar_wait(my_full + 8 * sg, pg);
+        const uint32_t slot = my_slots + (uint32_t)sg * (uint32_t)kStageSlotBytes;
+        float4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = lds128(slot + src_off[j]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(my_empty + 8 * sg);     // release: the reads above are ordered before it
+        if (++sg == nsg) { sg = 0; pg ^= 1u; }
+        mbar_wait(a_empty + 8 * sa, pa ^ 1u);
+        tc_fence_after();
+        const uint32_t col = lane_base + a_ring + (uint32_t)sa * kAStageCols;
+        if constexpr (BF) {
+          // 32 K values of this row -> 16 packed bf16 words hi + 16 words lo (k even in the low half)
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float f[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+            for (int e = 0; e < 4; e += 2) {
+              const uint32_t h = cvt_bf16x2(f[e + 1], f[e]);
+              const float h0 = __uint_as_float(h << 16), h1 = __uint_as_float(h & 0xffff0000u);
+              hi[2 * j + e / 2] = h;
+              lo[2 * j + e / 2] = cvt_bf16x2(f[e + 1] - h1, f[e] - h0);
+            }
+          }
+          tc_st16(col, hi);
+          tc_st16(col + 16u, lo);
+        } else {
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {   // two 16-float halves keep the live registers down
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 fv = v[4 * hh + j];
+              const float f[4] = {fv.x, fv.y, fv.z, fv.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                hi[4 * j + e] = __float_as_uint(f[e]) & 0xffffe000u;
+                lo[4 * j + e] = __float_as_uint(f[e] - __uint_as_float(hi[4 * j + e]));
+              }
+            }
+            tc_st16(col + (uint32_t)(16 * hh), hi);
+            if (NSPLIT == 2) tc_st16(col + 32u + (uint32_t)(16 * hh), lo);
+          }
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_full + 8 * sa);       // 4 arrivals per K block
+        if (++sa == nsa) { sa = 0; pa ^= 1u; }
+      }
+    }
+    // =============================== epilogue ============================================
+    const int half = warp >> 2;
+    mbar_wait(accbar, 0);
+    tc_fence_after();
+    const int orow = row0 + q * 32 + lane;
+    const int ncol_half = c_out / 2;
+    const int col_begin = half * ncol_half;
+    const bool row_ok = orow < p.n_out;
+    const float *scale = p.scale, *shift = p.shift;
+    const int relu = p.relu;
+    for (int c0 = col_begin; c0 < col_begin + ncol_half; c0 += 16) {
+      float acc[16];
+      tc_ld16(tmem_base + lane_base + (uint32_t)c0, acc);
+      if (p.nmerge) {   // columns [c_out, 2 c_out) hold the hi x lo partial sums
+        float more[16];
+        tc_ld16(tmem_base + lane_base + (uint32_t)(c_out + c0), more);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) acc[e] += more[e];
+      }
+      if (row_ok) {
+        float *dst = p.out + (long long)orow * c_out + c0;
+        const float *res = p.residual ? p.residual + (long long)orow * c_out + c0 : nullptr;
+        const int ncols = min(16, col_begin + ncol_half - c0);
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          if (j < ncols) {
+            float y[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float t = acc[j + e];
+              if (scale) t *= __ldg(scale + c0 + j + e);
+              if (shift) t += __ldg(shift + c0 + j + e);
+              y[e] = t;
+            }
+            if (res) {
+              const float4 rv = __ldg(reinterpret_cast<const float4 *>(res + j));
+              y[0] += rv.x; y[1] += rv.y; y[2] += rv.z; y[3] += rv.w;
+            }
+            if (relu) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) y[e] = fmaxf(y[e], 0.f);
+            }
+            *reinterpret_cast<float4 *>(dst + j) = make_float4(y[0], y[1], y[2], y[3]);
+          }
+        }
+      }
+    }
+  } else if (warp == 8) {
+    // =============================== MMA issuer ==========================================
+    const uint32_t idesc = BF ? umma_idesc_bf16(kTileM, c_out) : umma_idesc_tf32(kTileM, c_out);
+    const uint32_t idesc2 = BF ? umma_idesc_bf16(kTileM, 2 * c_out)   // merged [W_hi | W_lo] operand
+                               : umma_idesc_tf32(kTileM, 2 * c_out);
+    const int nmerge = p.nmerge;
+    int sa = 0, sb = 0;
+    uint32_t pa = 0, pb = 0;
+    for (int it = 0; it < n_iters; ++it) {
+      mbar_wait(a_full + 8 * sa, pa);
+      mbar_wait(b_full + 8 * sb, pb);   // BF16: already complete for the second K block of a stage
+      tc_fence_after();
+      const bool last = it == n_iters - 1;
+      const bool b_done = !BF || (it & 1) || last;   // the weight stage is free after its last K block
+      if (elect_one_sync()) {
+        const uint32_t a_hi = a_ring + (uint32_t)sa * kAStageCols;   // lane 0, column offset
+        const uint32_t a_lo = a_hi + (BF ? 16u : 32u);
+        const uint32_t bstage = smem_base + (uint32_t)sb * (uint32_t)b_stage_bytes;
+        const uint64_t b_hi = umma_desc_sw128(bstage);
+        const uint64_t b_lo = umma_desc_sw128(bstage + b_part_bytes);
+        constexpr int KSTEPS = BF ? 2 : 4;           // 16 bf16 / 8 tf32 per MMA = 32 B of K either way
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+          const uint64_t badv = (uint64_t)(ks * 2 + (BF ? (it & 1) * 4 : 0));
+          const uint32_t aadv = (uint32_t)(ks * 8);
+          const uint32_t d = tmem_base;
+          const uint32_t first = (it == 0 && ks == 0) ? 0u : 1u;
+          if (nmerge) {
+            if constexpr (BF) {
+              tc_mma_bf16_ts(d, a_hi + aadv, b_hi + badv, idesc2, first);
+              tc_mma_bf16_ts(d, a_lo + aadv, b_hi + badv, idesc, 1u);
+            } else {
+              tc_mma_tf32_ts(d, a_hi + aadv, b_hi + badv, idesc2, first);
+              tc_mma_tf32_ts(d, a_lo + aadv, b_hi + badv, idesc, 1u);
+            }
+          } else if constexpr (BF) {
+            tc_mma_bf16_ts(d, a_lo + aadv, b_hi + badv, idesc, first);
+            tc_mma_bf16_ts(d, a_hi + aadv, b_lo + badv, idesc, 1u);
+            tc_mma_bf16_ts(d, a_hi + aadv, b_hi + badv, idesc, 1u);
+          } else if (NSPLIT == 2) {
+            tc_mma_tf32_ts(d, a_lo + aadv, b_hi + badv, idesc, first);
+            tc_mma_tf32_ts(d, a_hi + aadv, b_lo + badv, idesc, 1u);
+            tc_mma_tf32_ts(d, a_hi + aadv, b_hi + badv, idesc, 1u);
+          } else {
+            tc_mma_tf32_ts(d, a_hi + aadv, b_hi + badv, idesc, first);
+          }
+        }
+        tc_commit(a_empty + 8 * sa);
+        if (b_done) tc_commit(b_empty + 8 * sb);
+        if (last) tc_commit(accbar);
+      }
+      __syncwarp();
+      if (++sa == nsa) { sa = 0; pa ^= 1u; }
+      if (b_done && ++sb == nsb) { sb = 0; pb ^= 1u; }
+    }
+  } else {
+    // =============================== weight loader =======================================
+    if (lane == 0) {
+      const int n_bstages = BF ? (n_iters + 1) / 2 : n_iters;
+      const char *src = reinterpret_cast<const char *>(p.wpacked);
+      int sb = 0;
+      uint32_t pb = 1;   // an untouched stage counts as released
+      for (int it = 0; it < n_bstages; ++it) {
+        mbar_wait(b_empty + 8 * sb, pb);
+        mbar_arrive_expect_tx(b_full + 8 * sb, (uint32_t)b_stage_bytes);
+        bulk_copy_g2s(smem_base + (uint32_t)sb * (uint32_t)b_stage_bytes, src, (uint32_t)b_stage_bytes,
+                      b_full + 8 * sb);
+        src += b_stage_bytes;
+        if (++sb == nsb) { sb = 0; pb ^= 1u; }
+      }
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
 // weight [K][Cin][Cout] fp32 -> packed [nkb][nsplit][Cout][32] in the swizzled smem image.  The K
 // axis is the concatenation over kernel offsets of the Cin channels (kk = k*Cin + ci), cut into
 // blocks of 32; element (n, c) of block kb sits at float index n*32 + (((c/4) ^ (n&7)) * 4) + (c%4).
@@ -899,14 +1239,15 @@ int spconv_forward_tc(const float *features, const float *weight, const float *p
   const int nbr_bytes = kvol * kTileM * 4;
   const int grid_tiles = (n_out + kTileM - 1) / kTileM;
 
-  // kernel variant: 4 (default: A in tensor memory) or 2 (both operands in shared memory; kept
-  // for A/B measurements).  BEVB200_SPCONV_TC_VARIANT=2 forces the latter.
+  // kernel variant: 5 (default: A in tensor memory, whole-line cp.async gather through swizzled
+  // staging slots), 4 (A in tensor memory, register gather + quad transposes) or 2 (both operands in
+  // shared memory).  BEVB200_SPCONV_TC_VARIANT=4 / 2 select the older ones for A/B measurements.
   static int forced = -1;
   if (forced < 0) {
     const char *e = getenv("BEVB200_SPCONV_TC_VARIANT");
     forced = e ? atoi(e) : 0;
   }
-  const int variant = (forced == 2 && !bf) ? 2 : 4;
+  const int variant = (forced == 2 && !bf) ? 2 : (forced == 4 ? 4 : 5);
 
   float *packed = nullptr;
   const float *wpacked = packed_in;
@@ -917,7 +1258,7 @@ int spconv_forward_tc(const float *features, const float *weight, const float *p
     wpacked = packed;
   }
 
-  if (variant == 4) {
+  if (variant == 4 || variant == 5) {
     TcParamsV4 p4;
     p4.features = features; p4.nbr = nbr; p4.scale = scale; p4.shift = shift; p4.residual = residual;
     p4.out = out; p4.n_in = n_in; p4.n_out = n_out; p4.c_in = c_in; p4.c_out = c_out; p4.kvol = kvol;
@@ -944,19 +1285,44 @@ int spconv_forward_tc(const float *features, const float *weight, const float *p
     if (p4.nsa > 4) p4.nsa = 4;
     p4.tmem_cols = 256;
     const int b_stage4 = (bf ? 2 : nsplit) * c_out * 128;
-    int nsb4 = (110 * 1024 - nbr_bytes - 1024) / b_stage4;
-    if (nsb4 > kMaxStages) nsb4 = kMaxStages;
-    if (nsb4 < 2) nsb4 = 2;
+    int nsb4;
+    size_t smem4;
+    if (variant == 5) {
+      // per CTA (two per SM): 1 KB alignment slack + weight ring + neighbour table + 4 quarters x nsg
+      // staging slots of 4 KB.  As many slots as fit beside a 2-stage weight ring, then the ring
+      // takes what is left.
+      const int budget = 111 * 1024;
+      p4.nbr_bytes = (nbr_bytes + 127) / 128 * 128;
+      const int avail = budget - 1024 - p4.nbr_bytes;
+      int nsg = (avail - 2 * b_stage4) / (4 * kStageSlotBytes);
+      if (nsg > kMaxGatherSlots) nsg = kMaxGatherSlots;
+      BEVB200_REQUIRE(nsg >= 2, "shared memory budget: no room for two gather slots");
+      p4.nsg = nsg;
+      nsb4 = (avail - nsg * 4 * kStageSlotBytes) / b_stage4;
+      if (nsb4 > kMaxStages) nsb4 = kMaxStages;
+      smem4 = (size_t)nsb4 * b_stage4 + p4.nbr_bytes + (size_t)nsg * 4 * kStageSlotBytes + 1024;
+    } else {
+      p4.nsg = 0;
+      p4.nbr_bytes = nbr_bytes;
+      nsb4 = (110 * 1024 - nbr_bytes - 1024) / b_stage4;
+      if (nsb4 > kMaxStages) nsb4 = kMaxStages;
+      if (nsb4 < 2) nsb4 = 2;
+      smem4 = (size_t)nsb4 * b_stage4 + nbr_bytes + 1024;
+    }
     p4.nsb = nsb4;
-    const size_t smem4 = (size_t)nsb4 * b_stage4 + nbr_bytes + 1024;
     auto launch = [&](auto kernel) -> int {
       BEVB200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
       kernel<<<grid_tiles, kV4Threads, smem4, st>>>(p4);
       BEVB200_CUDA(cudaGetLastError());
       return BEVB200_OK;
     };
-    const int lrc = bf ? launch(spconv_tc_kernel_v4<3>)
-                       : (nsplit == 2 ? launch(spconv_tc_kernel_v4<2>) : launch(spconv_tc_kernel_v4<1>));
+    int lrc;
+    if (variant == 5)
+      lrc = bf ? launch(spconv_tc_kernel_v5<3>)
+               : (nsplit == 2 ? launch(spconv_tc_kernel_v5<2>) : launch(spconv_tc_kernel_v5<1>));
+    else
+      lrc = bf ? launch(spconv_tc_kernel_v4<3>)
+               : (nsplit == 2 ? launch(spconv_tc_kernel_v4<2>) : launch(spconv_tc_kernel_v4<1>));
     if (lrc) return lrc;
     ++g_launch_count;
   } else {
