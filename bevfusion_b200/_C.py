@@ -55,6 +55,7 @@ _SIGNATURES = {
     "bevb200_rulebook_to_pairs": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P]),
     "bevb200_pairs_to_nbr": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P]),
     "bevb200_spconv_forward": (c_int, [_P, _P, _P] + [c_int] * 5 + [_P, _P, _P, c_int, c_int, _P, _P]),
+    "bevb200_spconv_padded_channels": (c_int, [c_int, c_int]),
     "bevb200_spconv_packed_weight_bytes": (c_size_t, [c_int] * 4),
     "bevb200_spconv_pack_weights": (c_int, [_P] + [c_int] * 4 + [_P, _P]),
     "bevb200_spconv_forward_packed": (c_int, [_P, _P, _P] + [c_int] * 5 + [_P, _P, _P, c_int, c_int, _P, _P]),

@@ -62,26 +62,25 @@ __global__ void rb_rank2row_kernel(const int32_t *__restrict__ indices, int n, C
 }
 
 // nbr[k, o] for SubM: input site = out site - pad + off*dil (stride 1, pad = k/2)
-__global__ void rb_subm_nbr_kernel(const int32_t *__restrict__ indices, int n, ConvGeom g,
-                                   const uint32_t *__restrict__ bits,
-                                   const uint32_t *__restrict__ prefix,
-                                   const int32_t *__restrict__ rank2row, int32_t *__restrict__ nbr) {
-  const long long total = (long long)n * g.kvol;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
-       t += (long long)gridDim.x * blockDim.x) {
-    int k = (int)(t / n), o = (int)(t % n);
-    int4 c = *reinterpret_cast<const int4 *>(indices + 4ll * o);
-    int kz = k % g.ksize[2], ky = (k / g.ksize[2]) % g.ksize[1], kx = k / (g.ksize[2] * g.ksize[1]);
-    int x = c.y - g.pad[0] + kx * g.dil[0];
-    int y = c.z - g.pad[1] + ky * g.dil[1];
-    int z = c.w - g.pad[2] + kz * g.dil[2];
+__global__ void __launch_bounds__(256)
+    rb_subm_nbr_kernel(const int32_t *__restrict__ indices, int n, ConvGeom g,
+                       const uint32_t *__restrict__ bits, const uint32_t *__restrict__ prefix,
+                       const int32_t *__restrict__ rank2row, int32_t *__restrict__ nbr) {
+  // grid (row tiles, kernel offsets): the offset is uniform per block, no per-element division
+  const int k = blockIdx.y;
+  const int kz = k % g.ksize[2], ky = (k / g.ksize[2]) % g.ksize[1], kx = k / (g.ksize[2] * g.ksize[1]);
+  const int dx = kx * g.dil[0] - g.pad[0], dy = ky * g.dil[1] - g.pad[1], dz = kz * g.dil[2] - g.pad[2];
+  int32_t *dst = nbr + (long long)k * n;
+  for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n; o += gridDim.x * blockDim.x) {
+    const int4 c = *reinterpret_cast<const int4 *>(indices + 4ll * o);
+    const int x = c.y + dx, y = c.z + dy, z = c.w + dz;
     int row = -1;
     if ((unsigned)c.x < (unsigned)g.batch && (unsigned)x < (unsigned)g.out_shape[0] &&
         (unsigned)y < (unsigned)g.out_shape[1] && (unsigned)z < (unsigned)g.out_shape[2]) {
       int r = site_rank(bits, prefix, flat_site(c.x, x, y, z, g.out_shape));
       if (r >= 0) row = rank2row ? rank2row[r] : r;
     }
-    nbr[t] = row;
+    dst[o] = row;
   }
 }
 
@@ -325,7 +324,7 @@ int bevb200_rulebook_fill(const int32_t *indices, int n_in, int batch_size,
     if (out_indices && out_indices != indices)
       BEVB200_CUDA(cudaMemcpyAsync(out_indices, indices, (size_t)n_in * 4 * sizeof(int32_t),
                                    cudaMemcpyDeviceToDevice, st));
-    BEVB200_LAUNCH(rb_subm_nbr_kernel, grid_for((long long)n_in * g.kvol, 256), 256, 0, st,
+    BEVB200_LAUNCH(rb_subm_nbr_kernel, dim3(grid_for(n_in, 256, kNumSMs * 2), g.kvol), 256, 0, st,
                    indices, n_in, g, w.bits, w.prefix, w.rank2row, nbr);
   } else {
     BEVB200_REQUIRE(out_indices != nullptr, "null out_indices");
@@ -356,7 +355,7 @@ int bevb200_rulebook_fill_subm_sorted(const int32_t *indices, int n, int batch_s
   }
   if (n == 0) return BEVB200_OK;
   BEVB200_REQUIRE(indices && nbr, "null argument");
-  BEVB200_LAUNCH(rb_subm_nbr_kernel, grid_for((long long)n * g.kvol, 256), 256, 0, (cudaStream_t)stream,
+  BEVB200_LAUNCH(rb_subm_nbr_kernel, dim3(grid_for(n, 256, kNumSMs * 2), g.kvol), 256, 0, (cudaStream_t)stream,
                  indices, n, g, w.bits, w.prefix, (const int32_t *)nullptr, nbr);
   return BEVB200_OK;
 }

@@ -163,21 +163,21 @@ int spconv_forward_simt(const float *features, const float *weight, const int32_
 }
 
 // ---- dense() ---------------------------------------------------------------------------
-__global__ void sparse_to_dense_kernel(const float *__restrict__ features,
-                                       const int32_t *__restrict__ indices, int n, int c,
-                                       int batch, int X, int Y, int Z, int z_major,
-                                       long long out_batch_stride, float *__restrict__ out) {
-  const long long total = (long long)n * c;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
-       t += (long long)gridDim.x * blockDim.x) {
-    int ch = (int)(t / n), i = (int)(t % n);  // row fastest: neighbouring sites -> nearby stores
-    int4 p = *reinterpret_cast<const int4 *>(indices + 4ll * i);  // (b, x, y, z)
+__global__ void __launch_bounds__(256)
+    sparse_to_dense_kernel(const float *__restrict__ features, const int32_t *__restrict__ indices,
+                           int n, int c, int batch, int X, int Y, int Z, int z_major,
+                           long long out_batch_stride, float *__restrict__ out) {
+  // grid (row tiles, channel groups): a thread handles one site and the channels ch0, ch0+gridDim.y, ..
+  // (site fastest across the warp: neighbouring sites -> nearby stores; no per-element division)
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int4 p = *reinterpret_cast<const int4 *>(indices + 4ll * i);  // (b, x, y, z)
     if ((unsigned)p.x >= (unsigned)batch || (unsigned)p.y >= (unsigned)X ||
         (unsigned)p.z >= (unsigned)Y || (unsigned)p.w >= (unsigned)Z)
       continue;
-    long long dst = z_major ? (((long long)ch * Z + p.w) * X + p.y) * Y + p.z
-                            : (((long long)ch * X + p.y) * Y + p.z) * Z + p.w;
-    out[p.x * out_batch_stride + dst] = features[(long long)i * c + ch];
+    const long long site = z_major ? ((long long)p.w * X + p.y) * Y + p.z : ((long long)p.y * Y + p.z) * Z + p.w;
+    const long long plane = (long long)X * Y * Z;
+    float *o = out + p.x * out_batch_stride + site;
+    for (int ch = blockIdx.y; ch < c; ch += gridDim.y) o[ch * plane] = features[(long long)i * c + ch];
   }
 }
 
@@ -191,6 +191,7 @@ int spconv_forward_tc(const float *features, const float *weight, const float *p
                       const float *scale, const float *shift, const float *residual, int relu,
                       int precision, float *out, cudaStream_t st);
 size_t spconv_packed_bytes(int c_in, int c_out, int kvol, int precision);
+int spconv_padded_channels(int c_in, int precision);
 int spconv_pack_weights(const float *weight, int c_in, int c_out, int kvol, int precision,
                         float *packed, cudaStream_t st);
 }
@@ -214,6 +215,10 @@ int bevb200_spconv_forward(const float *features, const float *weight, const int
     return spconv_forward_tc(features, weight, nullptr, nbr, n_in, n_out, c_in, c_out, kernel_volume,
                              scale, shift, residual, relu, precision, out, st);
   BEVB200_REQUIRE(false, "unknown precision mode");
+}
+
+int bevb200_spconv_padded_channels(int c_in, int precision) {
+  return spconv_padded_channels(c_in, precision);
 }
 
 size_t bevb200_spconv_packed_weight_bytes(int c_in, int c_out, int kernel_volume, int precision) {
@@ -264,8 +269,8 @@ int bevb200_sparse_to_dense(const float *features, const int32_t *indices, int n
   }
   if (n == 0) return BEVB200_OK;
   BEVB200_REQUIRE(features && indices, "null argument");
-  BEVB200_LAUNCH(sparse_to_dense_kernel, grid_for((long long)n * c, 256), 256, 0, st, features,
-                 indices, n, c, batch_size, X, Y, Z, z_major, out_batch_stride, out);
+  BEVB200_LAUNCH(sparse_to_dense_kernel, dim3(grid_for(n, 256, kNumSMs), c < 32 ? c : 32), 256, 0, st,
+                 features, indices, n, c, batch_size, X, Y, Z, z_major, out_batch_stride, out);
   return BEVB200_OK;
 }
 

@@ -1135,8 +1135,9 @@ __global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v5(const TcPar
 // weight [K][Cin][Cout] fp32 -> packed [nkb][nsplit][Cout][32] in the swizzled smem image.  The K
 // axis is the concatenation over kernel offsets of the Cin channels (kk = k*Cin + ci), cut into
 // blocks of 32; element (n, c) of block kb sits at float index n*32 + (((c/4) ^ (n&7)) * 4) + (c%4).
-__global__ void spconv_pack_weights_kernel(const float *__restrict__ w, int kvol, int c_in, int c_out,
-                                           int nkb, int nsplit, float *__restrict__ packed) {
+// c_in_eff >= c_in is the (zero-padded) channel count the kernel runs with.
+__global__ void spconv_pack_weights_kernel(const float *__restrict__ w, int kvol, int c_in, int c_in_eff,
+                                           int c_out, int nkb, int nsplit, float *__restrict__ packed) {
   const long long total = (long long)nkb * c_out * 32;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
        t += (long long)gridDim.x * blockDim.x) {
@@ -1144,8 +1145,8 @@ __global__ void spconv_pack_weights_kernel(const float *__restrict__ w, int kvol
     const int n = (int)((t / 32) % c_out);
     const int kb = (int)(t / (32ll * c_out));
     const int kk = kb * 32 + c;
-    const int k = kk / c_in, ci = kk % c_in;
-    const float v = k < kvol ? w[((long long)k * c_in + ci) * c_out + n] : 0.f;
+    const int k = kk / c_in_eff, ci = kk % c_in_eff;
+    const float v = (k < kvol && ci < c_in) ? w[((long long)k * c_in + ci) * c_out + n] : 0.f;
     const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
     const long long blk = (long long)kb * nsplit;
     const int pos = n * 32 + ((((c >> 2) ^ (n & 7)) << 2) | (c & 3));
@@ -1161,8 +1162,8 @@ int spconv_forward_simt(const float *features, const float *weight, const int32_
 
 // BF16x3 weights: packed [nb64][hi | lo][Cout][64 bf16] in the swizzled smem image; K index
 // kk = kb64*64 + c (c in 0..63), 16-byte chunk (c / 8) XOR (n & 7), element (c % 8) inside the chunk.
-__global__ void spconv_pack_weights_bf16_kernel(const float *__restrict__ w, int kvol, int c_in, int c_out,
-                                                int nb64, uint16_t *__restrict__ packed) {
+__global__ void spconv_pack_weights_bf16_kernel(const float *__restrict__ w, int kvol, int c_in, int c_in_eff,
+                                                int c_out, int nb64, uint16_t *__restrict__ packed) {
   const long long total = (long long)nb64 * c_out * 64;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
        t += (long long)gridDim.x * blockDim.x) {
@@ -1170,8 +1171,8 @@ __global__ void spconv_pack_weights_bf16_kernel(const float *__restrict__ w, int
     const int n = (int)((t / 64) % c_out);
     const int kb = (int)(t / (64ll * c_out));
     const int kk = kb * 64 + c;
-    const int k = kk / c_in, ci = kk % c_in;
-    const float v = k < kvol ? w[((long long)k * c_in + ci) * c_out + n] : 0.f;
+    const int k = kk / c_in_eff, ci = kk % c_in_eff;
+    const float v = (k < kvol && ci < c_in) ? w[((long long)k * c_in + ci) * c_out + n] : 0.f;
     uint32_t u = __float_as_uint(v);
     u += 0x7fffu + ((u >> 16) & 1u);
     const uint32_t hb = u >> 16;
@@ -1184,34 +1185,79 @@ __global__ void spconv_pack_weights_bf16_kernel(const float *__restrict__ w, int
   }
 }
 
-static bool tc_shape_ok(int c_in, int c_out, int kvol) {
-  return (c_out == 16 || c_out == 32 || c_out == 64 || c_out == 128) &&
-         (c_in == 16 || c_in == 32 || c_in == 64 || c_in == 128) && kvol >= 1 && kvol <= 27;
+// kernel variant: 5 (default: A in tensor memory, whole-line cp.async gather through swizzled
+// staging slots), 4 (A in tensor memory, register gather + quad transposes) or 2 (both operands in
+// shared memory).  BEVB200_SPCONV_TC_VARIANT=4 / 2 select the older ones for A/B measurements.
+static int tc_variant(bool bf) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char *e = getenv("BEVB200_SPCONV_TC_VARIANT");
+    forced = e ? atoi(e) : 0;
+  }
+  return (forced == 2 && !bf) ? 2 : (forced == 4 ? 4 : 5);
 }
 
-static int tc_nkb(int c_in, int kvol) { return (kvol * c_in + kKBlock - 1) / kKBlock; }
+// Input channels the kernel runs with: narrow inputs (conv_input: Cin = 5) are zero-padded to 8
+// (v5; 16 for the older variants), other counts to the next power of two up to 128.  0 = no
+// tensor-core form.
+static int tc_cin_eff(int c_in, int precision) {
+  const int lo = tc_variant(precision == BEVB200_PREC_BF16X3) == 5 ? 8 : 16;
+  for (int e = lo; e <= 128; e <<= 1)
+    if (c_in <= e) return e;
+  return 0;
+}
+
+static bool tc_shape_ok(int c_in, int c_out, int kvol, int precision) {
+  return (c_out == 16 || c_out == 32 || c_out == 64 || c_out == 128) && c_in >= 1 &&
+         tc_cin_eff(c_in, precision) != 0 && kvol >= 1 && kvol <= 27;
+}
+
+int spconv_padded_channels(int c_in, int precision) {
+  if (precision == BEVB200_PREC_FP32 || c_in < 1) return c_in;
+  const int e = tc_cin_eff(c_in, precision);
+  return e ? e : c_in;
+}
+
+static int tc_nkb(int c_in_eff, int kvol) { return (kvol * c_in_eff + kKBlock - 1) / kKBlock; }
 
 size_t spconv_packed_bytes(int c_in, int c_out, int kvol, int precision) {
-  if (!tc_shape_ok(c_in, c_out, kvol)) return 0;
+  if (!tc_shape_ok(c_in, c_out, kvol, precision)) return 0;
+  const int ce = tc_cin_eff(c_in, precision);
   if (precision == BEVB200_PREC_BF16X3)
-    return (size_t)((tc_nkb(c_in, kvol) + 1) / 2) * 2 * c_out * 64 * sizeof(uint16_t);
+    return (size_t)((tc_nkb(ce, kvol) + 1) / 2) * 2 * c_out * 64 * sizeof(uint16_t);
   const int nsplit = precision == BEVB200_PREC_TF32X3 ? 2 : 1;
-  return (size_t)tc_nkb(c_in, kvol) * nsplit * c_out * 32 * sizeof(float);
+  return (size_t)tc_nkb(ce, kvol) * nsplit * c_out * 32 * sizeof(float);
 }
 
 int spconv_pack_weights(const float *weight, int c_in, int c_out, int kvol, int precision,
                         float *packed, cudaStream_t st) {
+  const int ce = tc_cin_eff(c_in, precision);
   if (precision == BEVB200_PREC_BF16X3) {
-    const int nb64 = (tc_nkb(c_in, kvol) + 1) / 2;
+    const int nb64 = (tc_nkb(ce, kvol) + 1) / 2;
     BEVB200_LAUNCH(spconv_pack_weights_bf16_kernel, grid_for((long long)nb64 * c_out * 64, 256), 256, 0, st,
-                   weight, kvol, c_in, c_out, nb64, (uint16_t *)packed);
+                   weight, kvol, c_in, ce, c_out, nb64, (uint16_t *)packed);
     return BEVB200_OK;
   }
   const int nsplit = precision == BEVB200_PREC_TF32X3 ? 2 : 1;
-  const int nkb = tc_nkb(c_in, kvol);
+  const int nkb = tc_nkb(ce, kvol);
   BEVB200_LAUNCH(spconv_pack_weights_kernel, grid_for((long long)nkb * c_out * 32, 256), 256, 0, st,
-                 weight, kvol, c_in, c_out, nkb, nsplit, packed);
+                 weight, kvol, c_in, ce, c_out, nkb, nsplit, packed);
   return BEVB200_OK;
+}
+
+// [n, c_in] -> [n, c_eff] rows, zero padded (c_eff a multiple of 4: 16-byte aligned rows)
+__global__ void spconv_pad_rows_kernel(const float *__restrict__ in, int n, int c_in, int c_eff,
+                                       float *__restrict__ out) {
+  const long long total = (long long)n * (c_eff / 4);
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int g4 = (int)(t % (c_eff / 4));
+    const long long r = t / (c_eff / 4);
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) v[e] = 4 * g4 + e < c_in ? in[r * c_in + 4 * g4 + e] : 0.f;
+    *reinterpret_cast<float4 *>(out + r * c_eff + 4 * g4) = make_float4(v[0], v[1], v[2], v[3]);
+  }
 }
 
 // `packed` may be null: the weights are then packed into a stream-ordered temporary.
@@ -1219,10 +1265,12 @@ int spconv_forward_tc(const float *features, const float *weight, const float *p
                       const int32_t *nbr, int n_in, int n_out, int c_in, int c_out, int kvol,
                       const float *scale, const float *shift, const float *residual, int relu,
                       int precision, float *out, cudaStream_t st) {
-  const bool ok = tc_shape_ok(c_in, c_out, kvol) && ((uintptr_t)features % 16 == 0) &&
+  const int c_in_real = c_in;
+  const int c_eff = tc_shape_ok(c_in, c_out, kvol, precision) ? tc_cin_eff(c_in, precision) : 0;
+  const bool ok = c_eff != 0 && (c_eff != c_in || (uintptr_t)features % 16 == 0) &&
                   ((uintptr_t)out % 16 == 0) && (residual == nullptr || (uintptr_t)residual % 16 == 0);
   if (!ok) {
-    // shapes the UMMA tile cannot take (e.g. conv_input, Cin = 5): exact-fp32 SIMT kernel
+    // shapes / alignments the UMMA path cannot take: exact-fp32 SIMT kernel
     if (weight == nullptr) {
       snprintf(g_last_error, sizeof(g_last_error), "spconv_forward: shape needs the unpacked weights");
       return BEVB200_EINVAL;
@@ -1231,6 +1279,16 @@ int spconv_forward_tc(const float *features, const float *weight, const float *p
                                residual, relu, out, st);
   }
   const bool bf = precision == BEVB200_PREC_BF16X3;
+  const int variant = tc_variant(bf);
+  float *padded = nullptr;
+  if (c_eff != c_in) {   // e.g. conv_input (Cin = 5 -> 8): zero-padded copy of the rows, padded weights
+    BEVB200_CUDA(cudaMallocAsync((void **)&padded, (size_t)(n_in > 0 ? n_in : 1) * c_eff * sizeof(float), st));
+    if (n_in > 0)
+      BEVB200_LAUNCH(spconv_pad_rows_kernel, grid_for((long long)n_in * (c_eff / 4), 256), 256, 0, st, features,
+                     n_in, c_in, c_eff, padded);
+    features = padded;
+    c_in = c_eff;
+  }
   const int nsplit = precision == BEVB200_PREC_TF32X3 ? 2 : 1;   // tf32 parts (unused in BF16 mode)
   const int nkb = tc_nkb(c_in, kvol);
   int cin_shift = 0;
@@ -1239,21 +1297,11 @@ int spconv_forward_tc(const float *features, const float *weight, const float *p
   const int nbr_bytes = kvol * kTileM * 4;
   const int grid_tiles = (n_out + kTileM - 1) / kTileM;
 
-  // kernel variant: 5 (default: A in tensor memory, whole-line cp.async gather through swizzled
-  // staging slots), 4 (A in tensor memory, register gather + quad transposes) or 2 (both operands in
-  // shared memory).  BEVB200_SPCONV_TC_VARIANT=4 / 2 select the older ones for A/B measurements.
-  static int forced = -1;
-  if (forced < 0) {
-    const char *e = getenv("BEVB200_SPCONV_TC_VARIANT");
-    forced = e ? atoi(e) : 0;
-  }
-  const int variant = (forced == 2 && !bf) ? 2 : (forced == 4 ? 4 : 5);
-
   float *packed = nullptr;
   const float *wpacked = packed_in;
   if (packed_in == nullptr) {
-    BEVB200_CUDA(cudaMallocAsync((void **)&packed, spconv_packed_bytes(c_in, c_out, kvol, precision), st));
-    int rc = spconv_pack_weights(weight, c_in, c_out, kvol, precision, packed, st);
+    BEVB200_CUDA(cudaMallocAsync((void **)&packed, spconv_packed_bytes(c_in_real, c_out, kvol, precision), st));
+    int rc = spconv_pack_weights(weight, c_in_real, c_out, kvol, precision, packed, st);
     if (rc) return rc;
     wpacked = packed;
   }
@@ -1349,6 +1397,7 @@ int spconv_forward_tc(const float *features, const float *weight, const float *p
     }
   }
   if (packed) BEVB200_CUDA(cudaFreeAsync(packed, st));
+  if (padded) BEVB200_CUDA(cudaFreeAsync(padded, st));
   return BEVB200_OK;
 }
 

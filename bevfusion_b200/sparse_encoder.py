@@ -1,12 +1,17 @@
 """SparseEncoder -- mirror of mmdet3d/models/backbones/sparse_encoder.py:11-217 (the VoxelNet
 middle encoder of BEVFusion's LiDAR branch), without mmcv / mmdet.  Same constructor, same
 sub-module names (conv_input, encoder_layers.encoder_layer{i}, conv_out) and state_dict."""
+import os
+
 import torch
 from torch import nn
 
 from . import spconv
 from .sparse_block import SparseBasicBlock, bn_scale_shift, make_sparse_convmodule
 from .spconv import ops as sp_ops
+
+
+_SIDE_STREAMS = {}   # device -> stream the rulebooks are built on (fused eval path)
 
 
 class SparseEncoder(nn.Module):
@@ -40,6 +45,7 @@ class SparseEncoder(nn.Module):
                                                      indice_key="subm1", conv_type="SubMConv3d")
         encoder_out_channels = self.make_encoder_layers(make_sparse_convmodule, norm_cfg,
                                                         self.base_channels, block_type=block_type)
+        self.overlap_rulebooks = os.environ.get("BEVB200_RULEBOOK_STREAM", "1") != "0"
         self.conv_out = make_sparse_convmodule(encoder_out_channels, self.output_channels,
                                                kernel_size=(1, 1, 3), stride=(1, 1, 2),
                                                norm_cfg=norm_cfg, padding=0,
@@ -80,6 +86,15 @@ class SparseEncoder(nn.Module):
         return conv(x, scale=s, shift=t, relu=True, precision=precision)
 
     def _forward_fused(self, x, precision, dense_out=None):
+        if self.overlap_rulebooks:
+            # rulebooks on a side stream (see SparseConvolution._rulebook): their kernels and the
+            # host waits for the strided convs' output counts hide behind the queued convolutions
+            dev = x.features.device
+            side = _SIDE_STREAMS.get(dev)
+            if side is None:
+                side = _SIDE_STREAMS[dev] = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))    # the voxel coordinates are ready
+            x.indice_dict["__rulebook_stream__"] = side
         x = self._convmodule_fused(self.conv_input, x, precision)
         for stage in self.encoder_layers:
             for block in stage:

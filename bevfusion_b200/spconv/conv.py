@@ -122,10 +122,27 @@ class SparseConvolution(SparseModule):
                 input.indice_dict[key] = datas
         if datas is not None:
             return datas[2], datas[5]
-        rb, out_shape = ops.get_rulebook(indices, input.batch_size, input.spatial_shape,
-                                         self.kernel_size, self.stride, self.padding,
-                                         self.dilation, self.output_padding, self.subm,
-                                         self.transposed)
+        side = input.indice_dict.get("__rulebook_stream__")
+        if side is None:
+            rb, out_shape = ops.get_rulebook(indices, input.batch_size, input.spatial_shape,
+                                             self.kernel_size, self.stride, self.padding,
+                                             self.dilation, self.output_padding, self.subm,
+                                             self.transposed)
+        else:
+            # The rulebook depends on the indices only, not on the features: build it on a side
+            # stream so its kernels -- and the host wait for the output count of a strided conv --
+            # overlap with the convolutions already queued on the main stream (SparseEncoder's
+            # fused path sets this up; the convs wait on `rb.ready`).
+            main = torch.cuda.current_stream(indices.device)
+            with torch.cuda.stream(side):
+                rb, out_shape = ops.get_rulebook(indices, input.batch_size, input.spatial_shape,
+                                                 self.kernel_size, self.stride, self.padding,
+                                                 self.dilation, self.output_padding, self.subm,
+                                                 self.transposed)
+                rb.ready = torch.cuda.Event()
+                rb.ready.record(side)
+            for t in (rb.nbr, rb.outids):
+                t.record_stream(main)
         # (outids, indices, indice_pairs, indice_pair_num, spatial_shape) as conv.py:176-182,
         # with the Rulebook object in the indice_pairs slot, plus the output shape
         datas = (rb.outids, indices, rb, None, input.spatial_shape, out_shape)
@@ -149,6 +166,10 @@ class SparseConvolution(SparseModule):
             out_tensor.grid = input.grid
             return out_tensor
         rb, out_spatial_shape = self._rulebook(input)
+        ready = getattr(rb, "ready", None)
+        if ready is not None:                       # built on the side stream: order this stream after it
+            torch.cuda.current_stream(features.device).wait_event(ready)
+            rb.ready = None
         fused = scale is not None or shift is not None or residual is not None or relu
         if fused or not torch.is_grad_enabled() or not (features.requires_grad or self.weight.requires_grad):
             if self.bias is not None:

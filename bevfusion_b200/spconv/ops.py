@@ -229,6 +229,12 @@ def sparse_conv(features, weight, nbr, n_out, scale=None, shift=None, residual=N
     with torch.cuda.device(dev):
         out = torch.empty((n_out, c_out), dtype=torch.float32, device=dev)
         if packed is not None and precision != PREC_FP32:
+            # narrow inputs (conv_input: 5 channels) run zero-padded; pad here with the caching
+            # allocator instead of letting the library take a stream-ordered temporary per call
+            c_pad = _C.lib().bevb200_spconv_padded_channels(c_in, int(precision))
+            if c_pad != c_in:
+                features = torch.nn.functional.pad(features, (0, c_pad - c_in))
+                c_in = c_pad
             rc = _C.lib().bevb200_spconv_forward_packed(
                 _C.ptr(features), _C.ptr(packed), _C.ptr(nbr), n_in, int(n_out), c_in, c_out, kvol,
                 _C.ptr(scale), _C.ptr(shift), _C.ptr(residual), int(bool(relu)), int(precision),

@@ -344,9 +344,15 @@ BEVB200_API int bevb200_spconv_forward(const float *features, const float *weigh
  * axis, tf32 hi / lo parts); bevb200_spconv_forward() builds it into a stream-ordered temporary
  * on every call, these entry points let a caller with static weights (eval mode) do it once.
  * bevb200_spconv_packed_weight_bytes() returns 0 when (c_in, c_out, kernel_volume, precision)
- * has no tensor-core form (c_in, c_out in {16,32,64,128}, kernel_volume <= 27, precision TF32X3
- * or TF32); such shapes go through bevb200_spconv_forward(), which falls back to the fp32
- * SIMT kernel on the GPU. */
+ * has no tensor-core form (c_out in {16,32,64,128}, c_in <= 128, kernel_volume <= 27, precision
+ * TF32X3, TF32 or BF16X3); such shapes go through bevb200_spconv_forward(), which falls back to
+ * the fp32 SIMT kernel on the GPU.
+ * Input channels are zero-padded to bevb200_spconv_padded_channels(c_in, precision) = 8, 16, 32,
+ * 64 or 128 (SparseEncoder.conv_input: 5 -> 8): the packed image already contains the padding,
+ * so the image packed for c_in is also the image for the padded count.  A caller that passes
+ * features with fewer channels than that gets them copied into a stream-ordered padded temporary
+ * on every call; passing rows that are already padded (and the padded count as c_in) avoids it. */
+BEVB200_API int bevb200_spconv_padded_channels(int c_in, int precision);
 BEVB200_API size_t bevb200_spconv_packed_weight_bytes(int c_in, int c_out, int kernel_volume, int precision);
 BEVB200_API int bevb200_spconv_pack_weights(const float *weight, int c_in, int c_out, int kernel_volume,
                                 int precision, float *packed, void *stream);
