@@ -99,6 +99,10 @@ class ClockSampler:
         return dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum summed over the 21 sparse-conv launches of one frame, from
+# the committed ncu pass (profiles/r1_launches_v5.md); not measured in this process
+ENC_TRAFFIC_BYTES = 1.4428e9
+
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
@@ -349,23 +353,24 @@ def run_ours(args, rank, world, local_rank):
     op_gbs = pool_bytes / (op_ms * 1e-3) / 1e9
     enc_tflops = flops / (stages["encoder_ms"] * 1e-3) / 1e12
     # `traffic`: dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed
-    # ncu --set full capture (profiles/r1_ncu_full_final.md), not measured in this process
+    # ncu pass (profiles/r1_launches_v5.md), not measured in this process
     roof_pool = dict(kernel="bevpool_fwd_tma_kernel<20,PERM> (plan API: gather through perm + zero-fill fused; + cells, fix-up)",
                      bound="hbm", achieved=round(pool_gbs, 1), peak=peaks["hbm_gbs"], unit="GB/s",
-                     frac=round(pool_gbs / peaks["hbm_gbs"], 4), traffic=683.8e6, ms=round(pool_ms, 4),
+                     frac=round(pool_gbs / peaks["hbm_gbs"], 4), traffic=677.3e6, ms=round(pool_ms, 4),
                      algorithmic_bytes=pool_bytes, peak_source=peaks["source"])
     roof_pool_op = dict(kernel="bevpool_fwd_tma_kernel<20,SORTED> (drop-in bev_pool_forward on sorted rows; + memset, fix-up)",
                         bound="hbm", achieved=round(op_gbs, 1), peak=peaks["hbm_gbs"], unit="GB/s",
                         frac=round(op_gbs / peaks["hbm_gbs"], 4), traffic=None, ms=round(op_ms, 4),
                         algorithmic_bytes=pool_bytes, peak_source=peaks["source"])
-    roof_enc = dict(kernel="spconv_tc_kernel_v4<2> x20 + spconv_simt x1 (whole SparseEncoder incl. rulebooks, dense)",
+    roof_enc = dict(kernel="spconv_tc_kernel_v5<3> x21 (whole SparseEncoder incl. rulebooks on the side stream, dense)",
                     bound="tensor", achieved=round(enc_tflops, 3), peak=peaks["bf16_tflops_sustained"], unit="TFLOP/s",
-                    frac=round(enc_tflops / peaks["bf16_tflops_sustained"], 5), traffic=1.49e9,
+                    frac=round(enc_tflops / peaks["bf16_tflops_sustained"], 5), traffic=ENC_TRAFFIC_BYTES,
                     ms=round(stages["encoder_ms"], 4), algorithmic_flops=flops, pairs=pairs,
                     peak_source=peaks["source"],
-                    note="useful FLOPs = sum 2*pairs*Cin*Cout; issued tensor work is 3x (3xTF32 split) on TF32 "
-                         "MMAs whose dense peak is half the bf16 peak used here; traffic = sum over the 20 "
-                         "tensor-core convs of the ncu capture")
+                    note="useful FLOPs = sum 2*pairs*Cin*Cout over real (non-missing) neighbour pairs; the kernel issues "
+                         "3 (2 when the hi|lo weight images are merged) bf16 MMAs per fp32 product (BF16x3 split) and "
+                         "also multiplies the zero rows of missing neighbours; traffic = sum over the 21 tensor-core "
+                         "convs of dram__bytes_read+write in profiles/r1_launches_v5.md")
     # hard_voxelize + mean: algorithmic bytes 4*F*N (points) + M*(4*P*F + 16) (voxels, coors, num) -- latency bound
     n_pts, m_vox = int(pts.shape[0]), int(v.shape[0])
     vox_bytes = 4 * 5 * n_pts + m_vox * (4 * 10 * 5 + 16)
@@ -384,7 +389,8 @@ def run_ours(args, rank, world, local_rank):
         "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": 1, "parallelism": "sample-parallel x%d" % world,
-                   "spconv_precision": {None: "tf32x3 (tcgen05, 3xTF32 split; default)", 0: "fp32 (SIMT)", 1: "tf32x3", 2: "tf32"}[args.precision],
+                   "spconv_precision": {None: "bf16x3 (tcgen05 kind::f16, bf16 hi/lo split of fp32 operands, fp32 accumulate; default)",
+                                        0: "fp32 (SIMT)", 1: "tf32x3", 2: "tf32", 3: "bf16x3"}[args.precision],
                    "l2": "inputs larger than L2: the 638 MB feature volume streams through L2 every step",
                    "bev_pool_plan": "rank/sort/interval tables cached per calibration (static geometry)",
                    "kept_rows": hp.n_kept, "intervals": hp.n_intervals},
@@ -523,7 +529,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", type=int, default=None, help="spconv precision: 0 fp32, 1 tf32x3, 2 tf32")
+    ap.add_argument("--precision", type=int, default=None, help="spconv precision: 0 fp32, 1 tf32x3, 2 tf32, 3 bf16x3 (default)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU baseline leg (profiling runs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

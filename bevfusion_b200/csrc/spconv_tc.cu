@@ -58,7 +58,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "WAIT_LOOP:\n\t"
+#ifdef BEVB200_TC_NOHINT
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+#else
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n\t"   // suspend, do not spin
+#endif
       "@p bra WAIT_DONE;\n\t"
       "bra WAIT_LOOP;\n\t"
       "WAIT_DONE:\n\t}"
@@ -400,6 +404,8 @@ struct TcParamsV4 {
   int nmerge;         // A_hi x [W_hi | W_lo] as ONE N = 2*c_out MMA (see the MMA issuer)
   int nsg;            // v5: gather staging slots per row quarter (2..4, 4 KB each)
   int nbr_bytes;      // v5: bytes of the neighbour table in shared memory (multiple of 128)
+  int csz;            // v5: thread-block cluster size (1, 2 or 4): weight stages are multicast
+  int dbg;            // timing diagnostics only (BEVB200_TC_DBG): 1 no staging reads, 2 no gather, 4 no MMA
 };
 
 __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16]) {
@@ -820,9 +826,13 @@ __global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v4(const TcPar
 constexpr int kStageSlotBytes = 32 * 128;   // one quarter's rows of one K block
 constexpr int kMaxGatherSlots = 4;
 
-__device__ __forceinline__ void cp_async16_zfill(uint32_t dst_smem, const void *src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes)
-               : "memory");
+// 16-byte cp.async; `row` < 0 = the ignore-src form: nothing is read, the 16 bytes are zero-filled
+__device__ __forceinline__ void cp_async16_row(uint32_t dst_smem, unsigned long long src, int row) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.lt.s32 p, %2, 0;\n\t"
+      "cp.async.cg.shared.global [%0], [%1], 16, p;\n\t}"
+      ::"r"(dst_smem), "l"(src), "r"(row) : "memory");
 }
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
@@ -840,7 +850,7 @@ __global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v5(const TcPar
   uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
   constexpr bool BF = NSPLIT == 3;
   constexpr int NPART = BF ? 2 : NSPLIT;
-  const int c_out = p.c_out, nsa = p.nsa, nsb = p.nsb, nsg = p.nsg, n_iters = p.nkb;
+  const int c_out = p.c_out, nsa = p.nsa, nsb = p.nsb, nsg = p.nsg, n_iters = p.nkb, csz = p.csz;
   const int b_part_bytes = c_out * 128;
   const int b_stage_bytes = NPART * b_part_bytes;
   __shared__ uint64_t bars[4 * kMaxStages + 1 + 8 * kMaxGatherSlots];
@@ -864,7 +874,7 @@ __global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v5(const TcPar
     }
     for (int s = 0; s < nsb; ++s) {
       mbar_init(b_full + 8 * s, 1);
-      mbar_init(b_empty + 8 * s, 1);
+      mbar_init(b_empty + 8 * s, csz);   // released by the MMA warp of every CTA of the cluster
     }
     for (int s = 0; s < 4 * kMaxGatherSlots; ++s) {
       mbar_init(g_full + 8 * s, 32);   // every lane of the gather warp: cp.async arrive (noinc)
@@ -880,7 +890,9 @@ __global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v5(const TcPar
   }
   tc_fence_before();
   __syncthreads();
+  if (csz > 1) cluster_sync_all();        // peers' barriers are initialised before any multicast
   tc_fence_after();
+  const uint16_t cmask = (uint16_t)((1u << csz) - 1u);
   const uint32_t tmem_base = tmem_base_s;
   const uint32_t a_ring = tmem_base + (uint32_t)p.acc_cols;            // column offset of A stage 0
   constexpr uint32_t kAStageCols = BF ? 32u : (uint32_t)NSPLIT * 32u;   // BF16: 16 cols hi | 16 cols lo
@@ -890,14 +902,14 @@ __global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v5(const TcPar
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     {
       // neighbour table of the tile: all (<= 14) loads of a thread are issued before any is used
-      constexpr int kPer = (27 * kTileM + kTcProducerThreads - 1) / kTcProducerThreads;
-      const int n_tab = p.kvol * kTileM, n_out = p.n_out, n_in = p.n_in;
+      constexpr int kPer = (28 * kTileM + kTcProducerThreads - 1) / kTcProducerThreads;
+      const int n_real = p.kvol * kTileM, n_tab = n_real + kTileM, n_out = p.n_out, n_in = p.n_in;   // + a row of -1
       int tv[kPer];
 #pragma unroll
       for (int u = 0; u < kPer; ++u) {
         const int i = tid + u * kTcProducerThreads;
         const int k = i >> 7, rr = i & 127, o = row0 + rr;
-        tv[u] = (i < n_tab && o < n_out) ? __ldg(p.nbr + (long long)k * n_out + o) : -1;
+        tv[u] = (i < n_real && o < n_out) ? __ldg(p.nbr + (long long)k * n_out + o) : -1;
       }
 #pragma unroll
       for (int u = 0; u < kPer; ++u) {
@@ -916,7 +928,7 @@ __global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v5(const TcPar
       const uint32_t row_bytes = (uint32_t)p.c_in * 4u;
       const char *features = reinterpret_cast<const char *>(p.features);
       const int32_t *nb_oct = nbr_s + q * 32 + 8 * m;      // the 8 rows of this lane's octet: two int4
-      const int cin_shift = p.cin_shift, cin_mask = p.c_in - 1, kvol = p.kvol;
+      const int cin_shift = p.cin_shift, cin_mask = p.c_in - 1;
       uint32_t dst_off[8];                                  // row (8m + t), swizzled chunk c ^ t
 #pragma unroll
       for (int t = 0; t < 8; ++t) dst_off[t] = (uint32_t)((8 * m + t) * 128 + ((c ^ t) << 4));
@@ -924,21 +936,20 @@ __global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v5(const TcPar
       uint32_t pg = 0;
       for (int it = 0; it < n_iters; ++it) {
         const int kk = it * kKBlock + 4 * c;               // first K index of this lane's chunk
-        const int k = kk >> cin_shift;
-        const char *base = features + ((kk & cin_mask) << 2);
-        int4 i0 = make_int4(-1, -1, -1, -1), i1 = i0;
-        if (k < kvol) {
-          i0 = *reinterpret_cast<const int4 *>(nb_oct + k * kTileM);
-          i1 = *reinterpret_cast<const int4 *>(nb_oct + k * kTileM + 4);
-        }
+        const int k = kk >> cin_shift;                     // <= kvol: row kvol of the table is all -1
+        // features + channel offset as ONE opaque 64-bit value, so that each gather address below is a
+        // single IMAD.WIDE (row * row_bytes + base) instead of a multiply plus a 64-bit add
+        unsigned long long base = reinterpret_cast<unsigned long long>(features) + (unsigned)((kk & cin_mask) << 2);
+        asm volatile("" : "+l"(base));
+        const int4 *nb = reinterpret_cast<const int4 *>(nb_oct + k * kTileM);
+        const int4 i0 = nb[0], i1 = nb[1];
         const int src[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
         mbar_wait(my_empty + 8 * sg, pg ^ 1u);             // slot released by the convert warp
         const uint32_t slot = my_slots + (uint32_t)sg * (uint32_t)kStageSlotBytes;
+        if (!(p.dbg & 2)) {
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          const bool ok = src[t] >= 0;
-          cp_async16_zfill(slot + dst_off[t], base + (unsigned long long)(uint32_t)(ok ? src[t] : 0) * row_bytes,
-                           ok ? 16u : 0u);
+          for (int t = 0; t < 8; ++t)
+            cp_async16_row(slot + dst_off[t], base + (unsigned long long)(uint32_t)max(src[t], 0) * row_bytes, src[t]);
         }
         cp_async_mbar_arrive_noinc(my_full + 8 * sg);
         if (++sg == nsg) { sg = 0; pg ^= 1u; }
@@ -954,8 +965,13 @@ __global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v5(const TcPar
         mbar_wait(my_full + 8 * sg, pg);
         const uint32_t slot = my_slots + (uint32_t)sg * (uint32_t)kStageSlotBytes;
         float4 v[8];
+        if (!(p.dbg & 1)) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = lds128(slot + src_off[j]);
+          for (int j = 0; j < 8; ++j) v[j] = lds128(slot + src_off[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = make_float4((float)it, 1.f, (float)lane, 2.f);
+        }
         __syncwarp();
         if (lane == 0) mbar_arrive(my_empty + 8 * sg);     // release: the reads above are ordered before it
         if (++sg == nsg) { sg = 0; pg ^= 1u; }
@@ -1072,7 +1088,7 @@ __global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v5(const TcPar
         const uint64_t b_lo = umma_desc_sw128(bstage + b_part_bytes);
         constexpr int KSTEPS = BF ? 2 : 4;           // 16 bf16 / 8 tf32 per MMA = 32 B of K either way
 #pragma unroll
-        for (int ks = 0; ks < KSTEPS; ++ks) {
+        for (int ks = 0; ks < ((p.dbg & 4) ? 0 : KSTEPS); ++ks) {
           const uint64_t badv = (uint64_t)(ks * 2 + (BF ? (it & 1) * 4 : 0));
           const uint32_t aadv = (uint32_t)(ks * 8);
           const uint32_t d = tmem_base;
@@ -1098,7 +1114,9 @@ __global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v5(const TcPar
           }
         }
         tc_commit(a_empty + 8 * sa);
-        if (b_done) tc_commit(b_empty + 8 * sb);
+        if (b_done) {
+          if (csz > 1) tc_commit_mcast(b_empty + 8 * sb, cmask); else tc_commit(b_empty + 8 * sb);
+        }
         if (last) tc_commit(accbar);
       }
       __syncwarp();
@@ -1107,16 +1125,27 @@ __global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v5(const TcPar
     }
   } else {
     // =============================== weight loader =======================================
+    // Every CTA streams the whole weight tensor once per tile (515 tiles x 1.77 MB at C = 128): with the
+    // gather, the staging reads and the MMAs all disabled (BEVB200_TC_DBG=7) the kernel still takes
+    // 72 % of its time, i.e. the floor is the per-K-block synchronisation skeleton plus what every SM
+    // must ingest (weights: 16 KB per K block per CTA at C = 128, as much as the features).  Optional
+    // cluster mode: CTA rank r fetches slice r of a stage ONCE and multicasts it into the same ring slot
+    // of every CTA of the cluster (their b_full barriers count the bytes; a slot is rewritten only after
+    // the MMA warps of ALL cluster CTAs released it).  It halves the L2 reads but not the per-SM ingest
+    // and measured slower, so it is off by default.
     if (lane == 0) {
       const int n_bstages = BF ? (n_iters + 1) / 2 : n_iters;
-      const char *src = reinterpret_cast<const char *>(p.wpacked);
+      const uint32_t crank = csz > 1 ? cluster_ctarank() : 0u;
+      const uint32_t slice = (uint32_t)b_stage_bytes / (uint32_t)csz;
+      const char *src = reinterpret_cast<const char *>(p.wpacked) + crank * slice;
       int sb = 0;
       uint32_t pb = 1;   // an untouched stage counts as released
       for (int it = 0; it < n_bstages; ++it) {
         mbar_wait(b_empty + 8 * sb, pb);
         mbar_arrive_expect_tx(b_full + 8 * sb, (uint32_t)b_stage_bytes);
-        bulk_copy_g2s(smem_base + (uint32_t)sb * (uint32_t)b_stage_bytes, src, (uint32_t)b_stage_bytes,
-                      b_full + 8 * sb);
+        const uint32_t dst = smem_base + (uint32_t)sb * (uint32_t)b_stage_bytes + crank * slice;
+        if (csz > 1) bulk_copy_g2s_mcast(dst, src, slice, b_full + 8 * sb, cmask);
+        else bulk_copy_g2s(dst, src, slice, b_full + 8 * sb);
         src += b_stage_bytes;
         if (++sb == nsb) { sb = 0; pb ^= 1u; }
       }
@@ -1125,6 +1154,7 @@ __global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v5(const TcPar
   }
   tc_fence_before();
   __syncthreads();
+  if (csz > 1) cluster_sync_all();        // nobody leaves while a peer may still signal it
   if (warp == 8) {
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
@@ -1316,6 +1346,14 @@ int spconv_forward_tc(const float *features, const float *weight, const float *p
       const char *e = getenv("BEVB200_SPCONV_NMERGE");
       merge_env = e ? atoi(e) : 1;
     }
+    {
+      static int dbg_env = -1;
+      if (dbg_env < 0) {
+        const char *e = getenv("BEVB200_TC_DBG");
+        dbg_env = e ? atoi(e) : 0;
+      }
+      p4.dbg = dbg_env;
+    }
     p4.nmerge = (merge_env && (nsplit == 2 || bf) && c_out <= 64) ? 1 : 0;
     p4.acc_cols = p4.nmerge ? (2 * c_out < 32 ? 32 : 2 * c_out) : acc_cols;
     {
@@ -1340,10 +1378,18 @@ int spconv_forward_tc(const float *features, const float *weight, const float *p
       // staging slots of 4 KB.  As many slots as fit beside a 2-stage weight ring, then the ring
       // takes what is left.
       const int budget = 111 * 1024;
-      p4.nbr_bytes = (nbr_bytes + 127) / 128 * 128;
+      p4.nbr_bytes = ((kvol + 1) * kTileM * 4 + 127) / 128 * 128;   // + one all -1 row (K tail padding)
       const int avail = budget - 1024 - p4.nbr_bytes;
       int nsg = (avail - 2 * b_stage4) / (4 * kStageSlotBytes);
       if (nsg > kMaxGatherSlots) nsg = kMaxGatherSlots;
+      {
+        static int nsg_env = -1;
+        if (nsg_env < 0) {
+          const char *e = getenv("BEVB200_TC_NSG");
+          nsg_env = e ? atoi(e) : 0;
+        }
+        if (nsg_env >= 2 && nsg_env < nsg) nsg = nsg_env;
+      }
       BEVB200_REQUIRE(nsg >= 2, "shared memory budget: no room for two gather slots");
       p4.nsg = nsg;
       nsb4 = (avail - nsg * 4 * kStageSlotBytes) / b_stage4;
@@ -1358,10 +1404,38 @@ int spconv_forward_tc(const float *features, const float *weight, const float *p
       smem4 = (size_t)nsb4 * b_stage4 + nbr_bytes + 1024;
     }
     p4.nsb = nsb4;
+    // v5: thread-block clusters can multicast the weight stages (BEVB200_SPCONV_CLUSTER=2|4).  Measured:
+    // no gain (2.54 / 2.69 ms vs 2.41 ms for the 20 convs) -- the floor is what each SM has to ingest
+    // (16 KB of weights + 16 KB of features per K block per CTA at C = 128), not the L2 read rate, so
+    // the default stays 1.
+    static int csz_env = -1;
+    if (csz_env < 0) {
+      const char *e = getenv("BEVB200_SPCONV_CLUSTER");
+      csz_env = e ? atoi(e) : 0;
+    }
+    int csz = 1;
+    if (variant == 5) {
+      csz = csz_env ? csz_env : 1;
+      if (csz != 1 && csz != 2 && csz != 4) csz = 1;
+    }
+    p4.csz = csz;
+    const int grid4 = (grid_tiles + csz - 1) / csz * csz;
     auto launch = [&](auto kernel) -> int {
       BEVB200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
-      kernel<<<grid_tiles, kV4Threads, smem4, st>>>(p4);
-      BEVB200_CUDA(cudaGetLastError());
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3(grid4);
+      cfg.blockDim = dim3(kV4Threads);
+      cfg.dynamicSmemBytes = smem4;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = csz;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      BEVB200_CUDA(cudaLaunchKernelEx(&cfg, kernel, p4));
       return BEVB200_OK;
     };
     int lrc;

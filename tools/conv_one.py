@@ -19,9 +19,10 @@ for li, (cin, cout, subm, ks, st, pd) in enumerate(layers):
     if li in want:
         f = torch.randn(idx.shape[0], cin, device=dev)
         w = torch.randn(rb.nbr.shape[0], cin, cout, device=dev) / (cin * 5)
-        packed = ops.pack_weights(w, 1)
+        prec = int(os.environ.get("PREC", "3"))
+        packed = ops.pack_weights(w, prec)
         for _ in range(3):
-            ops.sparse_conv(f, w, rb.nbr, rb.n_out, precision=1, packed=packed)
+            ops.sparse_conv(f, w, rb.nbr, rb.n_out, precision=prec, packed=packed)
         torch.cuda.synchronize()
     if not subm:
         idx, shape = rb.outids, oshape
