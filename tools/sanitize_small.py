@@ -29,9 +29,29 @@ for (cin, cout) in ((16, 32), (64, 64), (5, 16)):
         rb, _ = ops.get_rulebook(ti, Bn, shape, ks, st, pd, 1, 0, subm)
         kv = rb.nbr.shape[0]
         w = torch.randn(kv, cin, cout, device=dev)
-        for prec in (0, 1, 2):
+        for prec in (0, 1, 2, 3):
             o = ops.sparse_conv(f, w, rb.nbr, rb.n_out, precision=prec)
+        o = ops.sparse_conv(f, w, rb.nbr, rb.n_out, precision=3, packed=ops.pack_weights(w, 3))
         ops.sparse_conv_backward(f, w, torch.randn_like(o), rb.nbr, precision=1)
         rb.pairs()
+# fused voxelize + mean, DynamicScatter fwd / bwd (all reductions), LiDAR depth images, in-place layouts
+from bevfusion_b200 import synthetic as S
+from bevfusion_b200.scatter_points import dynamic_scatter
+from bevfusion_b200.voxelize import voxel_layer, voxelize_mean_fused
+from bevfusion_b200.vtransform import points_to_depth
+vs, cr = [0.4, 0.5, 0.25], [-8.0, -6.0, -1.0, 8.0, 6.0, 3.0]
+pts = torch.from_numpy(S.uniform_cloud(3000, seed=1, margin=1.0, rng_range=cr)).to(dev)
+voxelize_mean_fused(pts, vs, cr, 4, 500, 1)
+coors = torch.zeros(pts.shape[0], 3, dtype=torch.int32, device=dev)
+voxel_layer.dynamic_voxelize(pts, coors, vs, cr, 3)
+for red in ("sum", "mean", "max"):
+    p = pts.clone().requires_grad_(True)
+    vf, vc = dynamic_scatter(p, coors, red)
+    vf.sum().backward()
+M = S.lidar_camera_matrices(2, (64, 176), batch=1)
+for kw in (dict(), dict(depth_input="one-hot", depth_bins=20, add_depth_features=True)):
+    points_to_depth([pts], M["lidar2image"].to(dev), M["img_aug_matrix"].to(dev), M["lidar_aug_matrix"].to(dev), (64, 176), **kw)
+buf = torch.zeros(2, 3 + 16 * 7, 20, 18, device=dev)
+ops.sparse_to_dense(torch.randn(n, 16, device=dev), ti, Bn, shape, z_major=True, out=buf[:, 3:])
 torch.cuda.synchronize()
 print("sanitize_small ok")
