@@ -7,28 +7,33 @@
 // once, after the fused BN / residual / ReLU epilogue.  The GEMM K axis is the concatenation over
 // the kernel offsets of the Cin channels, cut into blocks of 32 floats (one 128-byte swizzle row).
 //
-// Default kernel (spconv_tc_kernel_v4, two CTAs per SM, 10 warps each):
-//   warps 0-7  producers: gather the neighbour feature rows with coalesced 16-byte loads (4 lanes
-//              per row; quad-transposed with shuffles so that lane == row), split every value
-//              into tf32 hi + lo (3xTF32: a = hi + lo, hi = a & ~0x1fff) in registers and write
-//              both parts into TENSOR MEMORY with tcgen05.st (A ring of 2-3 stages, 4 K blocks
-//              prefetched in registers).  Missing neighbours become zero rows.
-//   warp 8     one elected lane issues tcgen05.mma.kind::tf32 with A from TMEM and B from shared
-//              memory (M128 x N=Cout x K8; per K step lo*hi + hi*lo + hi*hi, fp32 accumulate),
+// Default kernel (spconv_tc_kernel_v5, two CTAs per SM, 10 warps each; see the comment above it):
+//   warps 0-3  GATHER: cp.async.cg 16-byte copies of the neighbour feature rows, 8 lanes per row =
+//              whole 128-byte lines, zero fill (ignore-src) for missing neighbours, into XOR-swizzled
+//              4 KB shared-memory staging slots; completion is signalled on an mbarrier by the
+//              copies themselves (cp.async.mbarrier.arrive.noinc).
+//   warps 4-7  CONVERT: lane = row; 8 conflict-free LDS.128 fetch the row's 32 floats, which are
+//              split into two parts (BF16x3: bf16 hi + bf16 lo; 3xTF32: tf32 hi + lo) in registers
+//              and written into TENSOR MEMORY with tcgen05.st (A ring of 2-4 stages).
+//   warp 8     one elected lane issues tcgen05.mma (kind::f16 / kind::tf32) with A from TMEM and B
+//              from shared memory (M128 x N=Cout x 32 B of K; per K step lo*hi + hi*lo + hi*hi, or
+//              A_hi x [W_hi | W_lo] + A_lo x W_hi as two MMAs when Cout <= 64; fp32 accumulate),
 //              tcgen05.commit's the A / B ring slots back and finally the accumulator.
-//   warp 9     streams the weights: they are pre-packed in global memory as the exact K-major
-//              SWIZZLE_128B shared-memory image [hi | lo][Cout][128 B] per K block and fetched with
-//              one cp.async.bulk (TMA 1-D) per stage into an up-to-8-deep ring (optionally
-//              multicast across a thread-block cluster).
-//   epilogue   warps 0-7 read the accumulator(s) with tcgen05.ld (32 lanes x 16 columns; warps w
-//              and w+4 share TMEM lane quarter w and split the columns), apply scale / shift
-//              (folded BatchNorm1d), residual and ReLU, and store the row.
-// spconv_tc_kernel_v2 (both operands in shared memory, producers write the swizzled A tile) is
-// the previous generation, kept behind BEVB200_SPCONV_TC_VARIANT=2: ncu showed it shared-memory
-// bound (every M128 MMA re-reads its 4 KB A tile from smem), which is what moved A into TMEM.
+//   warp 9     streams the weights: pre-packed in global memory as the exact K-major SWIZZLE_128B
+//              shared-memory image [hi | lo][Cout][128 B] and fetched with one cp.async.bulk
+//              (TMA 1-D) per stage into a ring (optionally multicast across a thread-block cluster).
+//   epilogue   warps 0-7 read the accumulator with tcgen05.ld (32 lanes x 16 columns; warps w and
+//              w+4 share TMEM lane quarter w and split the columns), apply scale / shift (folded
+//              BatchNorm1d), residual and ReLU, and store the row.
+// Older generations stay selectable for A/B measurements (BEVB200_SPCONV_TC_VARIANT):
+//   4  spconv_tc_kernel_v4: same MMA / weight / epilogue roles, but 8 producer warps gather into
+//      registers (4 lanes per row), transpose with shuffles and split;
+//   2  spconv_tc_kernel_v2: both operands in shared memory -- ncu showed it shared-memory bound
+//      (every M128 MMA re-reads its 4 KB A tile), which is what moved A into TMEM.
 //
-// BEVB200_PREC_TF32X3 keeps fp32-class accuracy (measured 1e-6 .. 1e-5 relative) at 3 MMAs per K
-// step; BEVB200_PREC_TF32 issues only hi*hi (single-pass TF32, ~8e-4 relative).
+// Precision (all fp32 in, fp32 accumulate, fp32 out): BEVB200_PREC_BF16X3 (default; 5e-6 .. 8e-6 of
+// max|out| vs the float64 oracle), BEVB200_PREC_TF32X3 (1e-6 .. 1e-5), BEVB200_PREC_TF32 (single
+// pass, ~8e-4: below the 1e-4 parity bar, measurement only).
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -439,12 +444,6 @@ __device__ __forceinline__ uint32_t cvt_bf16x2(float hi, float lo) {
   uint32_t d;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
   return d;
-}
-// fp32 -> bf16 (round to nearest even), bit pattern in the low 16 bits
-__device__ __forceinline__ uint32_t bf16_bits(float f) {
-  uint32_t u = __float_as_uint(f);
-  u += 0x7fffu + ((u >> 16) & 1u);
-  return u >> 16;
 }
 __device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
                                                uint32_t idesc, uint32_t accumulate) {
