@@ -193,6 +193,35 @@ class HotPath:
         return total, pairs_total
 
 
+def conv_launch_times(hp, feats, coords, frames=5):
+    """CUDA-event time of every sparse-conv kernel launch of `frames` encoder passes (the events
+    bracket the library call on the launching stream).  Returns (ms per frame summed over the conv
+    launches, launches per frame)."""
+    from bevfusion_b200.spconv import ops as sp_ops
+    real = sp_ops.sparse_conv
+    evs = []
+
+    def timed(*a, **k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = real(*a, **k)
+        e1.record()
+        evs.append((e0, e1))
+        return out
+
+    with torch.no_grad():
+        hp.encoder(feats, coords, 1, precision=hp.precision)          # warm
+        sp_ops.sparse_conv = timed
+        try:
+            for _ in range(frames):
+                hp.encoder(feats, coords, 1, precision=hp.precision)
+        finally:
+            sp_ops.sparse_conv = real
+    torch.cuda.synchronize()
+    total = sum(a.elapsed_time(b) for a, b in evs)
+    return total / frames, len(evs) // frames
+
+
 def run_ours(args, rank, world, local_rank):
     from bevfusion_b200 import _C
     torch.cuda.set_device(local_rank)
@@ -380,7 +409,21 @@ def run_ours(args, rank, world, local_rank):
                     ms=round(stages["voxelize_ms"], 4), algorithmic_bytes=vox_bytes,
                     points_per_s=round(n_pts / (stages["voxelize_ms"] * 1e-3)), peak_source=peaks["source"],
                     note="latency bound: 40 MB of algorithmic traffic in ~10 dependent launches")
-    dominant = roof_enc if stages["encoder_ms"] >= stages["bev_pool_ms"] else roof_pool
+    # dominant kernel of the step: the tcgen05 sparse conv (21 launches per frame, ~3/4 of the step);
+    # its launches are timed one by one with CUDA events, achieved = useful FLOPs of those launches / that time
+    conv_ms, conv_launches = conv_launch_times(hp, feats, coords)
+    conv_tflops = flops / (conv_ms * 1e-3) / 1e12
+    roof_conv = dict(kernel="spconv_tc_kernel_v5<3> (tcgen05 implicit-GEMM sparse conv, BF16x3; %d launches per frame)" % conv_launches,
+                     bound="tensor", achieved=round(conv_tflops, 3), peak=peaks["bf16_tflops_sustained"], unit="TFLOP/s",
+                     frac=round(conv_tflops / peaks["bf16_tflops_sustained"], 5), traffic=ENC_TRAFFIC_BYTES,
+                     ms=round(conv_ms, 4), avg_launch_us=round(1e3 * conv_ms / max(conv_launches, 1), 2),
+                     launches_per_frame=conv_launches, algorithmic_flops=flops, pairs=pairs, peak_source=peaks["source"],
+                     note="achieved = sum over the frame's conv launches of 2*pairs*Cin*Cout (real neighbour pairs only) / "
+                          "their summed CUDA-event time; the kernel issues 2-3 bf16 MMAs per fp32 product (hi/lo split) and "
+                          "also multiplies the zero rows of missing neighbours, so the tensor pipe is busier than this "
+                          "fraction says (ncu: 36 % active at C=64, 64 % at C=128; profiles/r1_ncu_full_v5.md); traffic = "
+                          "dram bytes of those launches (profiles/r1_launches_v5.md)")
+    dominant = roof_conv if stages["encoder_ms"] >= stages["bev_pool_ms"] else roof_pool
     # the CPU baseline is timed on rank 0 at N = 1 only
     cpu = None if (args.no_cpu_baseline or world > 1) else cpu_baseline(n_steps=1)
     line = {

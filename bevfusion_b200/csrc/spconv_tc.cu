@@ -28,8 +28,8 @@
 // Older generations stay selectable for A/B measurements (BEVB200_SPCONV_TC_VARIANT):
 //   4  spconv_tc_kernel_v4: same MMA / weight / epilogue roles, but 8 producer warps gather into
 //      registers (4 lanes per row), transpose with shuffles and split;
-//   2  spconv_tc_kernel_v2: both operands in shared memory -- ncu showed it shared-memory bound
-//      (every M128 MMA re-reads its 4 KB A tile), which is what moved A into TMEM.
+//   (v2, both operands in shared memory, was removed: ncu showed it shared-memory bound -- every M128
+//   MMA re-reads its 4 KB A tile -- which is what moved A into TMEM; profiles/r1_conv_layers_v2.txt.)
 //
 // Precision (all fp32 in, fp32 accumulate, fp32 out): BEVB200_PREC_BF16X3 (default; 5e-6 .. 8e-6 of
 // max|out| vs the float64 oracle), BEVB200_PREC_TF32X3 (1e-6 .. 1e-5), BEVB200_PREC_TF32 (single
@@ -41,10 +41,8 @@
 namespace bevb200 {
 
 constexpr int kTcProducerThreads = 256;
-constexpr int kTcThreads = kTcProducerThreads + 32;
 constexpr int kTileM = 128;
 constexpr int kKBlock = 32;                       // floats per K block = one 128-byte swizzle row
-constexpr int kABlockBytes = kTileM * 128;        // one split part of the A stage: 16 KB
 
 // ---- PTX wrappers ----------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -164,226 +162,10 @@ __host__ __device__ inline uint32_t umma_idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// ---- v2: one tile per CTA, combined A+B stages, two CTAs per SM when the stages are small ----
-struct TcParamsV2 {
-  const float *features;
-  const float *wpacked;   // [K][nkb][nsplit][Cout][32] floats, swizzled smem image
-  const int32_t *nbr;
-  const float *scale, *shift, *residual;
-  float *out;
-  int n_in, n_out, c_in, c_out, kvol, relu;
-  int nkb;        // K blocks of 32 floats over the concatenated (offset, channel) axis
-  int cin_shift;  // log2(c_in): c_in is a power of two >= 16 on this path
-  int nstages;
-  int tmem_cols;  // power of two >= max(32, c_out)
-};
-
-template <int NSPLIT>
-__global__ void __launch_bounds__(kTcThreads, 2) spconv_tc_kernel_v2(const TcParamsV2 p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // align the stage area to 1024 B (SWIZZLE_128B atoms)
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
-  const int b_part_bytes = p.c_out * 128;                       // one split part of B: Cout x 128 B
-  const int stage_bytes = NSPLIT * (kABlockBytes + b_part_bytes);
-  __shared__ uint64_t bars[2 * 8 + 1];
-  __shared__ uint32_t tmem_base_s;
-  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[8]), accbar = smem_u32(&bars[16]);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int row0 = blockIdx.x * kTileM;
-  const int NS = p.nstages;
-
-  if (tid == 0) {
-    for (int s = 0; s < NS; ++s) {
-      mbar_init(full0 + 8 * s, kTcProducerThreads + 1);
-      mbar_init(empty0 + 8 * s, 1);
-    }
-    mbar_init(accbar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 8) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                 ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)p.tmem_cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = tmem_base_s;
-  const int n_iters = p.nkb;
-
-  if (warp < 8) {
-    // =============================== producers ===========================================
-    const int r = tid & 127, half = tid >> 7;
-    const uint32_t sw = (uint32_t)(r & 7);
-    const uint32_t row_off = (uint32_t)r * 128u;
-    // neighbour rows of this tile for every offset, staged once in shared memory
-    int32_t *nbr_s = reinterpret_cast<int32_t *>(smem + (size_t)NS * stage_bytes);
-    {
-      // neighbour table of the tile: all (<= 14) loads of a thread are issued before any is used
-      constexpr int kPer = (27 * kTileM + kTcProducerThreads - 1) / kTcProducerThreads;
-      int tv[kPer];
-#pragma unroll
-      for (int u = 0; u < kPer; ++u) {
-        const int i = tid + u * kTcProducerThreads;
-        const int k = i >> 7, rr = i & 127, o = row0 + rr;
-        tv[u] = (i < p.kvol * kTileM && o < p.n_out) ? __ldg(p.nbr + (long long)k * p.n_out + o) : -1;
-      }
-#pragma unroll
-      for (int u = 0; u < kPer; ++u) {
-        const int i = tid + u * kTcProducerThreads;
-        if (i < p.kvol * kTileM) nbr_s[i] = tv[u] >= p.n_in ? -1 : tv[u];
-      }
-    }
-    asm volatile("bar.sync 1, %0;" ::"n"(kTcProducerThreads) : "memory");
-
-    // K block `it` covers concatenated-K indices [32*it, 32*it+32); this thread owns 16 of them
-    // (4 float4 chunks), which lie inside ONE kernel offset because c_in % 16 == 0.
-    auto issue = [&](int it, float4 (&v)[4]) {
-      const int kk = it * kKBlock + half * 16;
-      const int k = kk >> p.cin_shift;
-      const int ch = kk & (p.c_in - 1);
-      const int src = k < p.kvol ? nbr_s[k * kTileM + r] : -1;
-      if (src >= 0) {
-        const float4 *q = reinterpret_cast<const float4 *>(p.features + (long long)src * p.c_in + ch);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = __ldg(q + j);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    };
-    constexpr int PD = 4;  // register prefetch distance (K blocks in flight per thread)
-    float4 v[PD][4];
-#pragma unroll
-    for (int j = 0; j < PD; ++j)
-      if (j < n_iters) issue(j, v[j]);
-    for (int it0 = 0; it0 < n_iters; it0 += PD) {
-#pragma unroll
-      for (int jj = 0; jj < PD; ++jj) {
-        const int it = it0 + jj;
-        if (it < n_iters) {
-          const int s = it % NS;
-          const uint32_t ph = (uint32_t)(it / NS) & 1u;
-          mbar_wait(empty0 + 8 * s, ph ^ 1u);
-          const uint32_t stage = smem_base + (uint32_t)s * (uint32_t)stage_bytes;
-          if (tid == 0) {
-            const uint32_t bbytes = (uint32_t)(NSPLIT * b_part_bytes);
-            mbar_arrive_expect_tx(full0 + 8 * s, bbytes);
-            const float *wsrc = p.wpacked + (long long)it * (long long)(NSPLIT * p.c_out * 32);
-            bulk_copy_g2s(stage + NSPLIT * kABlockBytes, wsrc, bbytes, full0 + 8 * s);
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t chunk = (uint32_t)(half * 4 + j);
-            const uint32_t off = row_off + ((chunk ^ sw) << 4);
-            uint4 hi;
-            hi.x = __float_as_uint(v[jj][j].x) & 0xffffe000u;
-            hi.y = __float_as_uint(v[jj][j].y) & 0xffffe000u;
-            hi.z = __float_as_uint(v[jj][j].z) & 0xffffe000u;
-            hi.w = __float_as_uint(v[jj][j].w) & 0xffffe000u;
-            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(stage + off), "r"(hi.x), "r"(hi.y),
-                         "r"(hi.z), "r"(hi.w) : "memory");
-            if (NSPLIT == 2) {
-              float4 lo;
-              lo.x = v[jj][j].x - __uint_as_float(hi.x);
-              lo.y = v[jj][j].y - __uint_as_float(hi.y);
-              lo.z = v[jj][j].z - __uint_as_float(hi.z);
-              lo.w = v[jj][j].w - __uint_as_float(hi.w);
-              asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stage + kABlockBytes + off),
-                           "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
-            }
-          }
-          fence_proxy_async();           // generic-proxy stores -> visible to the tensor core (async proxy)
-          mbar_arrive(full0 + 8 * s);
-          if (it + PD < n_iters) issue(it + PD, v[jj]);
-        }
-      }
-    }
-    // =============================== epilogue ============================================
-    mbar_wait(accbar, 0);
-    tc_fence_after();
-    const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int orow = row0 + q * 32 + lane;  // accumulator lane == output row of the tile
-    const int ncol_half = p.c_out / 2;      // warps q and q+4 split the columns
-    const int col_begin = (warp >> 2) * ncol_half;
-    for (int c0 = col_begin; c0 < col_begin + ncol_half; c0 += 16) {
-      float acc[16];
-      tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
-      if (orow < p.n_out) {
-        float *dst = p.out + (long long)orow * p.c_out + c0;
-        const float *res = p.residual ? p.residual + (long long)orow * p.c_out + c0 : nullptr;
-        const int ncols = min(16, col_begin + ncol_half - c0);
-#pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          if (j < ncols) {
-            float y[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float t = acc[j + e];
-              if (p.scale) t *= __ldg(p.scale + c0 + j + e);
-              if (p.shift) t += __ldg(p.shift + c0 + j + e);
-              y[e] = t;
-            }
-            if (res) {
-              float4 rv = __ldg(reinterpret_cast<const float4 *>(res + j));
-              y[0] += rv.x; y[1] += rv.y; y[2] += rv.z; y[3] += rv.w;
-            }
-            if (p.relu) {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) y[e] = fmaxf(y[e], 0.f);
-            }
-            *reinterpret_cast<float4 *>(dst + j) = make_float4(y[0], y[1], y[2], y[3]);
-          }
-        }
-      }
-    }
-  } else {
-    // =============================== MMA issuer (warp 8; lane 0 issues) ===================
-    const uint32_t idesc = umma_idesc_tf32(kTileM, p.c_out);
-    for (int it = 0; it < n_iters; ++it) {
-      const int s = it % NS;
-      const uint32_t ph = (uint32_t)(it / NS) & 1u;
-      mbar_wait(full0 + 8 * s, ph);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t stage = smem_base + (uint32_t)s * (uint32_t)stage_bytes;
-        const uint64_t a_hi = umma_desc_sw128(stage);
-        const uint64_t a_lo = umma_desc_sw128(stage + kABlockBytes);
-        const uint64_t b_hi = umma_desc_sw128(stage + NSPLIT * kABlockBytes);
-        const uint64_t b_lo = umma_desc_sw128(stage + NSPLIT * kABlockBytes + b_part_bytes);
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          const uint64_t adv = (uint64_t)(ks * 2);  // +32 B along K inside the 128-byte swizzle row
-          if (NSPLIT == 2) {
-            // small terms first, then the dominant product
-            tc_mma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc, (it > 0 || ks > 0) ? 1u : 0u);
-            tc_mma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc, 1u);
-            tc_mma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, 1u);
-          } else {
-            tc_mma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, (it > 0 || ks > 0) ? 1u : 0u);
-          }
-        }
-        tc_commit(empty0 + 8 * s);   // frees the smem slot once these MMAs have read it
-        if (it == n_iters - 1) tc_commit(accbar);   // accumulator complete -> epilogue
-      }
-      __syncwarp();
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 8) {
-    __syncwarp();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"((uint32_t)p.tmem_cols) : "memory");
-  }
-}
-
 constexpr int kMaxStages = 8;
 
 // ---- v4: A operand in TENSOR MEMORY (tcgen05.mma TS form) ------------------------------------
-// Measured on v2: with both operands in shared memory the M128 x N x K8 tf32 MMA re-reads the
+// Measured on v2 (removed): with both operands in shared memory the M128 x N x K8 tf32 MMA re-reads the
 // 4 KB A tile from smem on every instruction (3 per K step with the 3xTF32 split), which on top
 // of the producers' stores saturates the 128 B/clk shared-memory port -- the kernel was smem
 // bound, not tensor bound.  Here the producers write the split A rows straight from registers
@@ -1215,15 +997,16 @@ __global__ void spconv_pack_weights_bf16_kernel(const float *__restrict__ w, int
 }
 
 // kernel variant: 5 (default: A in tensor memory, whole-line cp.async gather through swizzled
-// staging slots), 4 (A in tensor memory, register gather + quad transposes) or 2 (both operands in
-// shared memory).  BEVB200_SPCONV_TC_VARIANT=4 / 2 select the older ones for A/B measurements.
+// staging slots) or 4 (A in tensor memory, register gather + quad transposes;
+// BEVB200_SPCONV_TC_VARIANT=4, kept for A/B measurements and covered by tests/test_spconv_gpu.py).
 static int tc_variant(bool bf) {
   static int forced = -1;
   if (forced < 0) {
     const char *e = getenv("BEVB200_SPCONV_TC_VARIANT");
     forced = e ? atoi(e) : 0;
   }
-  return (forced == 2 && !bf) ? 2 : (forced == 4 ? 4 : 5);
+  (void)bf;
+  return forced == 4 ? 4 : 5;
 }
 
 // Input channels the kernel runs with: narrow inputs (conv_input: Cin = 5) are zero-padded to 8
@@ -1335,7 +1118,7 @@ int spconv_forward_tc(const float *features, const float *weight, const float *p
     wpacked = packed;
   }
 
-  if (variant == 4 || variant == 5) {
+  {
     TcParamsV4 p4;
     p4.features = features; p4.nbr = nbr; p4.scale = scale; p4.shift = shift; p4.residual = residual;
     p4.out = out; p4.n_in = n_in; p4.n_out = n_out; p4.c_in = c_in; p4.c_out = c_out; p4.kvol = kvol;
@@ -1446,28 +1229,6 @@ int spconv_forward_tc(const float *features, const float *weight, const float *p
                : (nsplit == 2 ? launch(spconv_tc_kernel_v4<2>) : launch(spconv_tc_kernel_v4<1>));
     if (lrc) return lrc;
     ++g_launch_count;
-  } else {
-    TcParamsV2 p2;
-    p2.features = features; p2.nbr = nbr; p2.scale = scale; p2.shift = shift; p2.residual = residual;
-    p2.out = out; p2.n_in = n_in; p2.n_out = n_out; p2.c_in = c_in; p2.c_out = c_out; p2.kvol = kvol;
-    p2.relu = relu; p2.nkb = nkb; p2.cin_shift = cin_shift; p2.tmem_cols = acc_cols; p2.wpacked = wpacked;
-    const int stage_bytes = nsplit * (kABlockBytes + c_out * 128);
-    int ns = 2;
-    if (2 * stage_bytes + nbr_bytes + 1024 > 111 * 1024) {
-      ns = (215 * 1024 - nbr_bytes) / stage_bytes;
-      if (ns > 4) ns = 4;
-    }
-    p2.nstages = ns;
-    const size_t smem2 = (size_t)ns * stage_bytes + nbr_bytes + 1024;
-    if (nsplit == 2) {
-      BEVB200_CUDA(cudaFuncSetAttribute(spconv_tc_kernel_v2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem2));
-      BEVB200_LAUNCH(spconv_tc_kernel_v2<2>, grid_tiles, kTcThreads, smem2, st, p2);
-    } else {
-      BEVB200_CUDA(cudaFuncSetAttribute(spconv_tc_kernel_v2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem2));
-      BEVB200_LAUNCH(spconv_tc_kernel_v2<1>, grid_tiles, kTcThreads, smem2, st, p2);
-    }
   }
   if (packed) BEVB200_CUDA(cudaFreeAsync(packed, st));
   if (padded) BEVB200_CUDA(cudaFreeAsync(padded, st));

@@ -376,3 +376,39 @@ def test_half_features(cuda):
                                                pairs, num, outids.shape[0], 0, int(subm))
     assert out.dtype == torch.half
     assert rel_err(out.float().cpu().numpy(), gold) <= 2e-3      # one fp16 rounding of the result
+
+
+def test_previous_kernel_generation_still_correct(cuda):
+    """BEVB200_SPCONV_TC_VARIANT=4 (register gather + shuffle transposes, kept for A/B measurements) is
+    read once per process, so it is exercised in a child process: same parity bar as the default."""
+    import subprocess
+    import sys
+    if not tc_available(cuda):
+        pytest.skip("no tcgen05 path")
+    code = r"""
+import numpy as np, torch, oracle
+from bevfusion_b200.spconv import ops
+rng = np.random.default_rng(3)
+shape, B, n = [24, 20, 9], 2, 3000
+vol = B * shape[0] * shape[1] * shape[2]
+flat = rng.choice(vol, size=n, replace=False)
+idx = np.stack([flat // (shape[0] * shape[1] * shape[2]), (flat // (shape[1] * shape[2])) % shape[0],
+                (flat // shape[2]) % shape[1], flat % shape[2]], 1).astype(np.int32)
+dev = torch.device("cuda:0")
+for cin, cout in ((16, 32), (64, 64), (128, 128)):
+    feat = rng.standard_normal((n, cin)).astype(np.float32)
+    W = (rng.standard_normal((3, 3, 3, cin, cout)) / np.sqrt(cin * 9)).astype(np.float32)
+    gold, gids, _ = oracle.sparse_conv(feat, idx, B, shape, W, [3] * 3, [1] * 3, [1] * 3, [1] * 3, True, acc64=True)
+    rb, _ = ops.get_rulebook(torch.from_numpy(idx).to(dev), B, shape, 3, 1, 1, 1, 0, True)
+    for prec in (1, 3):
+        out = ops.sparse_conv(torch.from_numpy(feat).to(dev), torch.from_numpy(W).to(dev), rb.nbr, rb.n_out,
+                              precision=prec).cpu().numpy()
+        err = np.abs(out - gold).max() / np.abs(gold).max()
+        assert err <= 1e-4, (cin, cout, prec, err)
+print("variant-4 ok")
+"""
+    env = dict(os.environ, BEVB200_SPCONV_TC_VARIANT="4",
+               PYTHONPATH=os.pathsep.join([os.path.dirname(os.path.dirname(os.path.abspath(__file__)))]
+                                          + os.environ.get("PYTHONPATH", "").split(os.pathsep)))
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "variant-4 ok" in r.stdout, r.stdout + r.stderr
