@@ -35,6 +35,8 @@ def points_to_depth(points, lidar2image, img_aug_matrix, lidar_aug_matrix, image
             q[:, 2] = torch.arange(0.25, 2.25, 0.25, device=p.device).repeat(p.shape[0])
             expanded.append(q)
         points = expanded
+    for b, pts in enumerate(points):                    # no CPU fallback: fail before any allocation
+        _C.require_cuda(pts, "points[%d]" % b, torch.float32)
     dev = points[0].device
     F = int(points[0].shape[1])
     channels = (int(depth_bins) if one_hot else 1) + (F if add_depth_features else 0)
@@ -47,7 +49,6 @@ def points_to_depth(points, lidar2image, img_aug_matrix, lidar_aug_matrix, image
         ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=dev)
         for b in range(B):
             p = points[b]
-            _C.require_cuda(p, "points[%d]" % b, torch.float32)
             if p.shape[1] != F:
                 raise ValueError("all samples must have the same number of point features")
             rc = _C.lib().bevb200_depth_rasterize(

@@ -94,3 +94,60 @@ def test_geometry_and_synthetic_shapes():
     pts = S.lidar_cloud(seed=0, sweeps=2)
     assert pts.shape[1] == 5 and pts.dtype == np.float32
     assert len(np.arange(*S.CONFIGS["C2"]["dbound"])) == 118
+
+
+def test_size_queries_of_the_later_entry_points():
+    """pure host-side size arithmetic of the C ABI (no device needed)."""
+    from bevfusion_b200 import _C
+    L = _C.lib()
+    # input channels the tensor-core conv runs with: <= 8 -> 8 (conv_input: 5), else next power of two
+    for c_in, want in ((1, 8), (5, 8), (8, 8), (9, 16), (16, 16), (17, 32), (64, 64), (100, 128), (128, 128)):
+        for prec in (1, 2, 3):
+            assert L.bevb200_spconv_padded_channels(c_in, prec) == want
+        assert L.bevb200_spconv_padded_channels(c_in, 0) == c_in          # exact-fp32 path: no padding
+    assert L.bevb200_spconv_padded_channels(129, 3) == 129                 # no tensor-core form: unchanged
+    # the packed image of a padded shape is the image of the padded channel count
+    for prec in (1, 3):
+        assert L.bevb200_spconv_packed_weight_bytes(5, 16, 27, prec) == L.bevb200_spconv_packed_weight_bytes(8, 16, 27, prec) > 0
+    assert L.bevb200_spconv_packed_weight_bytes(64, 48, 27, 3) == 0        # c_out must be 16 / 32 / 64 / 128
+    assert L.bevb200_spconv_packed_weight_bytes(64, 64, 28, 3) == 0        # kernel volume <= 27
+    assert L.bevb200_spconv_packed_weight_bytes(128, 128, 27, 3) == 27 * 128 * 128 * 2 * 2   # bf16 hi + lo
+    assert L.bevb200_spconv_packed_weight_bytes(128, 128, 27, 1) == 27 * 128 * 128 * 2 * 4   # tf32 hi + lo
+    assert L.bevb200_depth_rasterize_workspace_bytes(6, 256, 704) == 6 * 256 * 704 * 4
+    assert L.bevb200_depth_rasterize_workspace_bytes(0, 256, 704) == 0
+    assert L.bevb200_dynamic_scatter_workspace_bytes(300000) > 300000 * (8 + 8 + 4 + 4 + 4 + 4 + 4)
+    assert L.bevb200_dynamic_scatter_workspace_bytes(0) > 0
+
+
+def test_output_view_validation():
+    """`out=` targets of the layout kernels: channel slices of a wider buffer are fine, anything that
+    is not dense inside a batch item is rejected before a pointer reaches the library."""
+    from bevfusion_b200.spconv.ops import _batch_stride_of
+    buf = torch.zeros(2, 336, 6, 5)
+    assert _batch_stride_of(buf[:, :80], (2, 80, 6, 5)) == 336 * 30
+    assert _batch_stride_of(buf[:, 80:], (2, 256, 6, 5)) == 336 * 30
+    assert _batch_stride_of(torch.zeros(1, 8, 3, 3), (1, 8, 3, 3)) == 72
+    with pytest.raises(ValueError):
+        _batch_stride_of(buf[:, :80, :, 1:], (2, 80, 6, 4))                # inner stride broken
+    with pytest.raises(ValueError):
+        _batch_stride_of(buf[:, :80], (2, 81, 6, 5))                      # wrong shape
+    with pytest.raises(ValueError):
+        _batch_stride_of(buf[:, :80].double(), (2, 80, 6, 5))             # wrong dtype
+
+
+def test_no_cpu_fallback_in_the_later_rows():
+    from bevfusion_b200.scatter_points import DynamicScatter
+    from bevfusion_b200.voxelize import voxel_layer, voxelize_mean_fused
+    from bevfusion_b200.vtransform import points_to_depth
+    pts, coors = torch.zeros(6, 5), torch.zeros(6, 3, dtype=torch.int32)
+    with pytest.raises(RuntimeError):
+        DynamicScatter([0.1] * 3, [0, 0, 0, 1, 1, 1], True)(pts, coors)
+    with pytest.raises(ValueError):
+        voxel_layer.dynamic_point_to_voxel_forward(pts, coors, "median")
+    with pytest.raises(RuntimeError):
+        voxelize_mean_fused(pts, [0.5] * 3, [0, 0, 0, 4, 4, 4], 5, 10)
+    eye = torch.eye(4).view(1, 1, 4, 4)
+    with pytest.raises(ValueError):
+        points_to_depth([pts], eye, eye, torch.eye(4).view(1, 4, 4), (8, 8), depth_input="histogram")
+    with pytest.raises(RuntimeError):
+        points_to_depth([pts], eye, eye, torch.eye(4).view(1, 4, 4), (8, 8))
