@@ -1,4 +1,6 @@
-"""Dev tool: per-role cycle counters of CTA 0 of the v4 sparse-conv kernel."""
+"""Dev tool: per-role cycle counters of CTA 0 of the v4 sparse-conv kernel.
+Needs a profiling build (BEVB200_BUILD_PROFILE=1 python bevfusion_b200/build.py --force) and
+BEVB200_SPCONV_TC_VARIANT=4; the default v5 kernel is analysed with BEVB200_TC_DBG (tools/conv_bench.py)."""
 import os, sys
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
 import torch
