@@ -166,3 +166,40 @@ def test_depth_oracle_last_point_wins():
     assert d[0, 0, 3, 2] == 1.0 and d[0, 4, 3, 2] == np.float32(0.4)     # point 3 beats 0 and 1
     assert d[0, 0, 0, 2] == 2.0 and d[0, 4, 0, 2] == np.float32(0.3)     # (4,1)/2 -> col 2,row 0
     assert (d[0, 0] != 0).sum() == 2
+
+
+def test_dynamic_scatter_oracle_properties():
+    """the restatement of dynamic_point_to_voxel_forward / _backward (scatter_points_cuda.cu:187-315):
+    lexicographic unique rows, negative rows dropped, permutation invariance, gradient routing."""
+    rng = np.random.default_rng(5)
+    n, c = 400, 3
+    coors = rng.integers(0, 5, (n, 3)).astype(np.int32)
+    coors[rng.random(n) < 0.1, 1] = -1
+    feats = rng.standard_normal((n, c)).astype(np.float32)
+    for red in ("sum", "mean", "max"):
+        r, oc, cmap, cnt = oracle.dynamic_scatter(feats, coors, red)
+        valid = (coors >= 0).all(1)
+        assert (cmap[~valid] == -1).all() and (cmap[valid] >= 0).all()
+        assert cnt.sum() == valid.sum() and (cnt > 0).all()
+        assert np.array_equal(oc, np.unique(coors[valid], axis=0))           # sorted unique rows
+        assert np.array_equal(oc[cmap[valid]], coors[valid])                 # the map points at the right voxel
+        perm = rng.permutation(n)
+        r2, oc2, cmap2, cnt2 = oracle.dynamic_scatter(feats[perm], coors[perm], red)
+        assert np.array_equal(oc2, oc) and np.array_equal(cnt2, cnt) and np.array_equal(cmap2, cmap[perm])
+        assert np.allclose(r2, r, rtol=1e-6, atol=1e-6)
+        g = rng.standard_normal(r.shape).astype(np.float32)
+        d = oracle.dynamic_scatter_backward(g, feats, r, cmap, cnt, red)
+        assert (d[~valid] == 0).all()
+        if red == "sum":
+            assert np.array_equal(d[valid], g[cmap[valid]])
+        elif red == "mean":
+            assert np.allclose(d[valid], g[cmap[valid]] / cnt[cmap[valid]][:, None])
+        else:
+            # every (voxel, channel) gradient lands on exactly one point: the first that attains the maximum
+            for v in range(r.shape[0]):
+                rows = np.nonzero(cmap == v)[0]
+                for ch in range(c):
+                    hit = rows[feats[rows, ch] == r[v, ch]]
+                    assert d[hit[0], ch] == g[v, ch] and (d[rows, ch] != 0).sum() <= 1
+    e = oracle.dynamic_scatter(feats[:0], coors[:0], "max")
+    assert e[0].shape == (0, c) and e[2].shape == (0,)
