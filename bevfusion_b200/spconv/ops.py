@@ -249,9 +249,10 @@ def sparse_conv(features, weight, nbr, n_out, scale=None, shift=None, residual=N
 
 
 def indice_conv(features, filters, indice_pairs, indice_pair_num, num_activate_out, inverse=False,
-                subm=False, precision=None):
+                subm=False, precision=None, bias=None):
     """Drop-in for ops.indice_conv (ops.py:128-152).  `indice_pairs` may be the reference
-    [K, 2, N] tensor (converted to a neighbour table first) or a Rulebook."""
+    [K, 2, N] tensor (converted to a neighbour table first) or a Rulebook.  `bias` [Cout] is added
+    in the conv epilogue (fused_indice_conv, ops.py:155-174)."""
     if filters.dtype not in (torch.float32, torch.half):
         raise NotImplementedError("filters must be fp32 or fp16")
     if isinstance(indice_pairs, Rulebook):
@@ -264,10 +265,19 @@ def indice_conv(features, filters, indice_pairs, indice_pair_num, num_activate_o
         # widened, the conv accumulates in fp32 on the tensor cores, and the result is narrowed
         # once -- at least as accurate as the reference's fp16 path
         out = sparse_conv(features.float().contiguous(), filters.float().contiguous(), nbr,
-                          int(num_activate_out), precision=precision)
+                          int(num_activate_out), shift=None if bias is None else bias.float().contiguous(),
+                          precision=precision)
         return out.half()
     return sparse_conv(features.contiguous(), filters.contiguous(), nbr, int(num_activate_out),
-                       precision=precision)
+                       shift=None if bias is None else bias.contiguous(), precision=precision)
+
+
+def fused_indice_conv(features, filters, bias, indice_pairs, indice_pair_num, num_activate_out, inverse,
+                      subm, precision=None):
+    """Drop-in for ops.fused_indice_conv (ops.py:155-174; fusedIndiceConvBatchNorm,
+    fused_spconv_ops.h:28-131): the output starts from the bias instead of zero."""
+    return indice_conv(features, filters, indice_pairs, indice_pair_num, num_activate_out, bool(inverse),
+                       bool(subm), precision=precision, bias=bias)
 
 
 def transpose_nbr(nbr, n_in):
@@ -315,8 +325,13 @@ def indice_conv_backward(features, filters, out_bp, indice_pairs, indice_pair_nu
                          subm=False, precision=None):
     """Drop-in for ops.indice_conv_backward (ops.py:177-189): returns [input_grad, filters_grad].
     `indice_pairs` may be the reference [K, 2, N] tensor or a Rulebook."""
+    if torch.half in (filters.dtype, features.dtype, out_bp.dtype):
+        # indice_conv_backward_half (ops.py:183-186): widened, computed with fp32 accumulation, narrowed once
+        din, dw = indice_conv_backward(features.float(), filters.float(), out_bp.float(), indice_pairs,
+                                       indice_pair_num, inverse, subm, precision)
+        return [din.half(), dw.half()]
     if filters.dtype != torch.float32:
-        raise NotImplementedError("only fp32 filters are implemented")
+        raise NotImplementedError("filters must be fp32 or fp16")
     if isinstance(indice_pairs, Rulebook):
         assert not inverse
         nbr = indice_pairs.nbr
@@ -355,7 +370,18 @@ class _SparseConvExt:
         return indice_conv_backward(features, filters, out_bp, indice_pairs, indice_pair_num,
                                     bool(inverse), bool(subm))
 
+    indice_conv_backward_half = indice_conv_backward_fp32      # half tensors are widened by the callee
+
+    @staticmethod
+    def fused_indice_conv_fp32(features, filters, bias, indice_pairs, indice_pair_num, num_activate_out,
+                               inverse, subm):
+        return fused_indice_conv(features, filters, bias, indice_pairs, indice_pair_num, num_activate_out,
+                                 inverse, subm)
+
+    fused_indice_conv_half = fused_indice_conv_fp32
+
     def __getattr__(self, name):
+        # 2-D / 4-D rulebooks, grid rulebooks, sparse max-pool: not used by any shipped config
         raise NotImplementedError("sparse_conv_ext.%s is outside the hot path" % name)
 
 

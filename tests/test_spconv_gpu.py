@@ -412,3 +412,32 @@ print("variant-4 ok")
                                           + os.environ.get("PYTHONPATH", "").split(os.pathsep)))
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "variant-4 ok" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent: never run on a device yet; "
+                   "non-strict so that it cannot stop the -x suite -- drop the marker once it has passed on a B200")
+def test_fused_indice_conv_and_half_backward_shims(cuda):
+    """the remaining sparse_conv_ext entry points a 3-D model can reach: fused_indice_conv_* (bias in the
+    epilogue; fused_spconv_ops.h:28-131) and indice_conv_backward_half (spconv_ops.h:363-456 on halves)."""
+    from bevfusion_b200.spconv import ops
+    rng = np.random.default_rng(11)
+    idx = random_sparse(800, [12, 10, 6], 2, seed=2)
+    feat = torch.from_numpy(rng.standard_normal((idx.shape[0], 16)).astype(np.float32)).to(cuda)
+    W = torch.from_numpy((rng.standard_normal((3, 3, 3, 16, 32)) / 12).astype(np.float32)).to(cuda)
+    bias = torch.from_numpy(rng.standard_normal(32).astype(np.float32)).to(cuda)
+    outids, pairs, num = ops.get_indice_pairs(torch.from_numpy(idx).to(cuda), 2, [12, 10, 6], 3, 1, 1, 1, 0, True)
+    ext = ops.sparse_conv_ext
+    plain = ext.indice_conv_fp32(feat, W, pairs, num, outids.shape[0], 0, 1)
+    fused = ext.fused_indice_conv_fp32(feat, W, bias, pairs, num, outids.shape[0], 0, 1)
+    assert float((fused - (plain + bias)).abs().max()) <= 1e-6 * float(plain.abs().max())
+    fused_h = ext.fused_indice_conv_half(feat.half(), W.half(), bias.half(), pairs, num, outids.shape[0], 0, 1)
+    assert fused_h.dtype == torch.half
+    assert float((fused_h.float() - fused).abs().max()) <= 2e-2 * float(fused.abs().max())
+    g = torch.randn_like(plain)
+    din, dw = ext.indice_conv_backward_fp32(feat, W, g, pairs, num, 0, 1)
+    din_h, dw_h = ext.indice_conv_backward_half(feat.half(), W.half(), g.half(), pairs, num, 0, 1)
+    assert din_h.dtype == torch.half and dw_h.dtype == torch.half and dw_h.shape == W.shape
+    assert float((din_h.float() - din).abs().max()) <= 2e-2 * float(din.abs().max())
+    assert float((dw_h.float() - dw).abs().max()) <= 2e-2 * float(dw.abs().max())
+    with pytest.raises(NotImplementedError):
+        ext.indice_maxpool_fp32
