@@ -59,10 +59,26 @@ _SIGNATURES = {
     "bevb200_spconv_packed_weight_bytes": (c_size_t, [c_int] * 4),
     "bevb200_spconv_pack_weights": (c_int, [_P] + [c_int] * 4 + [_P, _P]),
     "bevb200_spconv_forward_packed": (c_int, [_P, _P, _P] + [c_int] * 5 + [_P, _P, _P, c_int, c_int, _P, _P]),
+    "bevb200_spconv_split_channels": (c_int, [c_int]),
+    "bevb200_spconv_split_rows": (c_int, [_P, c_int, _P, c_int, _P, _P]),
+    "bevb200_spconv_split_weight_bytes": (c_size_t, [c_int] * 3),
+    "bevb200_spconv_pack_split_weights": (c_int, [_P] + [c_int] * 3 + [_P, _P]),
+    "bevb200_spconv_forward_split": (c_int, [_P, _P, _P, ctypes.c_longlong, c_int, c_int, _P] + [c_int] * 3
+                                     + [_P, _P, _P, c_int, _P, _P, _P]),
     "bevb200_rulebook_transpose": (c_int, [_P, c_int, c_int, c_int, _P, _P]),
     "bevb200_spconv_backward_workspace_bytes": (c_size_t, [c_int] * 3),
     "bevb200_spconv_backward": (c_int, [_P] * 5 + [c_int] * 6 + [_P, _P, _P, c_size_t, _P]),
     "bevb200_sparse_to_dense": (c_int, [_P, _P, c_int, c_int, c_int, _P, c_int, ctypes.c_longlong, _P, _P]),
+    "bevb200_encoder_create": (c_int, [c_int, _P, _P, c_int, _P]),
+    "bevb200_encoder_destroy": (None, [_P]),
+    "bevb200_encoder_param_bytes": (c_size_t, [_P]),
+    "bevb200_encoder_num_levels": (c_int, [_P]),
+    "bevb200_encoder_output_shape": (c_int, [_P, _P, _P]),
+    "bevb200_encoder_set_conv": (c_int, [_P, c_int, _P, _P, _P, _P, c_size_t, _P]),
+    "bevb200_encoder_level_caps": (c_int, [_P, c_int, c_int, _P, _P]),
+    "bevb200_encoder_workspace_bytes": (c_size_t, [_P, c_int, c_int, _P]),
+    "bevb200_encoder_forward": (c_int, [_P, _P, _P, _P, c_int, _P, c_int, _P, _P, ctypes.c_longlong, _P, _P,
+                                        c_size_t, _P, _P]),
 }
 
 

@@ -37,6 +37,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace bevb200 {
 
@@ -44,125 +45,16 @@ constexpr int kTcProducerThreads = 256;
 constexpr int kTileM = 128;
 constexpr int kKBlock = 32;                       // floats per K block = one 128-byte swizzle row
 
-// ---- PTX wrappers ----------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-#ifdef BEVB200_TC_NOHINT
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-#else
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n\t"   // suspend, do not spin
-#endif
-      "@p bra WAIT_DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "WAIT_DONE:\n\t}"
-      ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst_smem, const void *src, uint32_t bytes,
-                                              uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-      ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-// one elected lane of a fully converged warp (elect.sync): the compiler keeps the tcgen05 issue
-// sequence on the uniform datapath; an `if (lane == 0)` branch instead makes it wrap every
-// UTCHMMA in an ELECT / BRA.U.ANY waterfall loop (measured: ~100 clk per MMA issue)
-__device__ __forceinline__ bool elect_one_sync() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .pred P;\n\t"
-      "elect.sync _|P, 0xffffffff;\n\t"
-      "selp.b32 %0, 1, 0, P;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void bulk_copy_g2s_mcast(uint32_t dst_smem, const void *src, uint32_t bytes,
-                                                    uint32_t bar, uint16_t cta_mask) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
-      "[%0], [%1], %2, [%3], %4;"
-      ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar), "h"(cta_mask) : "memory");
-}
-__device__ __forceinline__ void tc_commit_mcast(uint32_t bar, uint16_t cta_mask) {
-  asm volatile(
-      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-      ::"r"(bar), "h"(cta_mask) : "memory");
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void fence_proxy_async() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_before() {
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_after() {
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
-               ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
-                                            uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, float v[16]) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
-        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
-        "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// UMMA shared-memory descriptor, K-major, SWIZZLE_128B (cute/arch/mma_sm100_desc.hpp layout):
-//   [0,14) start address >> 4, [16,30) leading byte offset >> 4 (unused for swizzled K-major),
-//   [32,46) stride byte offset >> 4 (= 1024 B between 8-row groups), [46,48) version = 1,
-//   [61,64) layout type = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-  uint64_t d = (uint64_t)((smem_addr & 0x3ffff) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-// instruction descriptor for kind::tf32: c=F32 (bit 4), a=b=TF32 (2 at bits 7, 10), both K-major,
-// N >> 3 at bit 17, M >> 4 at bit 24
-__host__ __device__ inline uint32_t umma_idesc_tf32(int M, int N) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
 
 constexpr int kMaxStages = 8;
+
+// Timing diagnostics (BEVB200_TC_DBG: 1 no staging reads, 2 no gather, 4 no MMA) produce WRONG outputs,
+// so they exist only in -DBEVB200_TC_PROFILE builds (BEVB200_BUILD_PROFILE=1 python bevfusion_b200/build.py).
+#ifdef BEVB200_TC_PROFILE
+#define TC_DBG(p, bit) ((p).dbg & (bit))
+#else
+#define TC_DBG(p, bit) 0
+#endif
 
 // ---- v4: A operand in TENSOR MEMORY (tcgen05.mma TS form) ------------------------------------
 // Measured on v2 (removed): with both operands in shared memory the M128 x N x K8 tf32 MMA re-reads the
@@ -216,16 +108,6 @@ __device__ __forceinline__ void tc_mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem,
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
       ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// instruction descriptor for kind::f16 with bf16 operands: c=F32 (bit 4), a=b=BF16 (1 at bits 7, 10)
-__host__ __device__ inline uint32_t umma_idesc_bf16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-// two fp32 -> packed bf16x2 (round to nearest even): `lo` lands in bits 0..15, `hi` in bits 16..31
-__device__ __forceinline__ uint32_t cvt_bf16x2(float hi, float lo) {
-  uint32_t d;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-  return d;
 }
 __device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
                                                uint32_t idesc, uint32_t accumulate) {
@@ -607,17 +489,6 @@ __global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v4(const TcPar
 constexpr int kStageSlotBytes = 32 * 128;   // one quarter's rows of one K block
 constexpr int kMaxGatherSlots = 4;
 
-// 16-byte cp.async; `row` < 0 = the ignore-src form: nothing is read, the 16 bytes are zero-filled
-__device__ __forceinline__ void cp_async16_row(uint32_t dst_smem, unsigned long long src, int row) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.lt.s32 p, %2, 0;\n\t"
-      "cp.async.cg.shared.global [%0], [%1], 16, p;\n\t}"
-      ::"r"(dst_smem), "l"(src), "r"(row) : "memory");
-}
-__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
-}
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
@@ -727,7 +598,7 @@ __global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v5(const TcPar
         const int src[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
         mbar_wait(my_empty + 8 * sg, pg ^ 1u);             // slot released by the convert warp
         const uint32_t slot = my_slots + (uint32_t)sg * (uint32_t)kStageSlotBytes;
-        if (!(p.dbg & 2)) {
+        if (!TC_DBG(p, 2)) {
 #pragma unroll
           for (int t = 0; t < 8; ++t)
             cp_async16_row(slot + dst_off[t], base + (unsigned long long)(uint32_t)max(src[t], 0) * row_bytes, src[t]);
@@ -746,7 +617,7 @@ __global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v5(const TcPar
         mbar_wait(my_full + 8 * sg, pg);
         const uint32_t slot = my_slots + (uint32_t)sg * (uint32_t)kStageSlotBytes;
         float4 v[8];
-        if (!(p.dbg & 1)) {
+        if (!TC_DBG(p, 1)) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[j] = lds128(slot + src_off[j]);
         } else {
@@ -869,7 +740,7 @@ __global__ void __launch_bounds__(kV4Threads, 2) spconv_tc_kernel_v5(const TcPar
         const uint64_t b_lo = umma_desc_sw128(bstage + b_part_bytes);
         constexpr int KSTEPS = BF ? 2 : 4;           // 16 bf16 / 8 tf32 per MMA = 32 B of K either way
 #pragma unroll
-        for (int ks = 0; ks < ((p.dbg & 4) ? 0 : KSTEPS); ++ks) {
+        for (int ks = 0; ks < (TC_DBG(p, 4) ? 0 : KSTEPS); ++ks) {
           const uint64_t badv = (uint64_t)(ks * 2 + (BF ? (it & 1) * 4 : 0));
           const uint32_t aadv = (uint32_t)(ks * 8);
           const uint32_t d = tmem_base;
@@ -996,17 +867,33 @@ __global__ void spconv_pack_weights_bf16_kernel(const float *__restrict__ w, int
   }
 }
 
-// kernel variant: 5 (default: A in tensor memory, whole-line cp.async gather through swizzled
-// staging slots) or 4 (A in tensor memory, register gather + quad transposes;
-// BEVB200_SPCONV_TC_VARIANT=4, kept for A/B measurements and covered by tests/test_spconv_gpu.py).
+// kernel variant (BEVB200_SPCONV_TC_VARIANT): 6 (default for BF16X3: spconv_v6.cu -- pre-split operands
+// gathered straight into UMMA tiles, R row tiles per weight stage, persistent CTAs), 5 (A in tensor
+// memory, whole-line cp.async gather through swizzled staging slots + convert warps; the default for the
+// TF32 modes) or 4 (A in tensor memory, register gather + quad transposes).  4 and 5 are kept for A/B
+// measurements and are covered by tests/test_spconv_gpu.py.
+int spconv_v6_cin_eff(int c_in);
+bool spconv_v6_shape_ok(int c_in, int c_out, int kvol);
+size_t spconv_v6_packed_bytes(int c_in, int c_out, int kvol);
+int spconv_v6_pack_weights(const float *weight, int c_in, int c_out, int kvol, void *packed, cudaStream_t st);
+int spconv_v6_split_rows(const float *features, int n_cap, const int32_t *n_dev, int c_in, void *split,
+                         cudaStream_t st);
+int spconv_v6_forward(const void *features_split, const void *packed, const int32_t *nbr, long long nbr_stride,
+                      int n_in, int n_out, const int32_t *n_out_dev, int c_in, int c_out, int kvol,
+                      const float *scale, const float *shift, const float *residual, int relu, float *out,
+                      void *out_split, cudaStream_t st);
+
 static int tc_variant(bool bf) {
   static int forced = -1;
   if (forced < 0) {
     const char *e = getenv("BEVB200_SPCONV_TC_VARIANT");
     forced = e ? atoi(e) : 0;
   }
-  (void)bf;
-  return forced == 4 ? 4 : 5;
+  if (forced == 4 || forced == 5) return forced;
+  return bf ? 6 : 5;
+}
+static bool use_v6(int c_in, int c_out, int kvol, int precision) {
+  return precision == BEVB200_PREC_BF16X3 && tc_variant(true) == 6 && spconv_v6_shape_ok(c_in, c_out, kvol);
 }
 
 // Input channels the kernel runs with: narrow inputs (conv_input: Cin = 5) are zero-padded to 8
@@ -1026,6 +913,7 @@ static bool tc_shape_ok(int c_in, int c_out, int kvol, int precision) {
 
 int spconv_padded_channels(int c_in, int precision) {
   if (precision == BEVB200_PREC_FP32 || c_in < 1) return c_in;
+  if (precision == BEVB200_PREC_BF16X3 && tc_variant(true) == 6) return c_in;   // the split pass pads
   const int e = tc_cin_eff(c_in, precision);
   return e ? e : c_in;
 }
@@ -1033,6 +921,7 @@ int spconv_padded_channels(int c_in, int precision) {
 static int tc_nkb(int c_in_eff, int kvol) { return (kvol * c_in_eff + kKBlock - 1) / kKBlock; }
 
 size_t spconv_packed_bytes(int c_in, int c_out, int kvol, int precision) {
+  if (use_v6(c_in, c_out, kvol, precision)) return spconv_v6_packed_bytes(c_in, c_out, kvol);
   if (!tc_shape_ok(c_in, c_out, kvol, precision)) return 0;
   const int ce = tc_cin_eff(c_in, precision);
   if (precision == BEVB200_PREC_BF16X3)
@@ -1043,6 +932,7 @@ size_t spconv_packed_bytes(int c_in, int c_out, int kvol, int precision) {
 
 int spconv_pack_weights(const float *weight, int c_in, int c_out, int kvol, int precision,
                         float *packed, cudaStream_t st) {
+  if (use_v6(c_in, c_out, kvol, precision)) return spconv_v6_pack_weights(weight, c_in, c_out, kvol, packed, st);
   const int ce = tc_cin_eff(c_in, precision);
   if (precision == BEVB200_PREC_BF16X3) {
     const int nb64 = (tc_nkb(ce, kvol) + 1) / 2;
@@ -1077,6 +967,35 @@ int spconv_forward_tc(const float *features, const float *weight, const float *p
                       const int32_t *nbr, int n_in, int n_out, int c_in, int c_out, int kvol,
                       const float *scale, const float *shift, const float *residual, int relu,
                       int precision, float *out, cudaStream_t st) {
+  if (use_v6(c_in, c_out, kvol, precision) && (uintptr_t)out % 16 == 0 &&
+      (residual == nullptr || (uintptr_t)residual % 16 == 0)) {
+    // generation 6 consumes the bf16 hi|lo image of the rows: build it (and, without pre-packed weights,
+    // the weight image) in stream-ordered temporaries.  SparseEncoder's fused path never comes here: its
+    // convs hand the image to each other (bevb200_encoder_forward).
+    const int ce = spconv_v6_cin_eff(c_in);
+    void *split = nullptr, *wtmp = nullptr;
+    int rc = BEVB200_OK;
+    if (cudaMallocAsync(&split, (size_t)(n_in > 0 ? n_in : 1) * ce * 4, st) != cudaSuccess) rc = BEVB200_ECUDA;
+    if (!rc && packed_in == nullptr) {
+      if (weight == nullptr) {
+        snprintf(g_last_error, sizeof(g_last_error), "spconv_forward: null weights");
+        rc = BEVB200_EINVAL;
+      } else if (cudaMallocAsync(&wtmp, spconv_v6_packed_bytes(c_in, c_out, kvol), st) != cudaSuccess) {
+        rc = BEVB200_ECUDA;
+      } else {
+        rc = spconv_v6_pack_weights(weight, c_in, c_out, kvol, wtmp, st);
+      }
+    }
+    if (!rc) rc = spconv_v6_split_rows(features, n_in, nullptr, c_in, split, st);
+    if (!rc)
+      rc = spconv_v6_forward(split, packed_in ? (const void *)packed_in : wtmp, nbr, n_out, n_in, n_out, nullptr, ce,
+                             c_out, kvol, scale, shift, residual, relu, out, nullptr, st);
+    if (rc == BEVB200_ECUDA && g_last_error[0] == 0)
+      snprintf(g_last_error, sizeof(g_last_error), "spconv_forward: stream-ordered allocation failed");
+    if (split) cudaFreeAsync(split, st);
+    if (wtmp) cudaFreeAsync(wtmp, st);
+    return rc;
+  }
   const int c_in_real = c_in;
   const int c_eff = tc_shape_ok(c_in, c_out, kvol, precision) ? tc_cin_eff(c_in, precision) : 0;
   const bool ok = c_eff != 0 && (c_eff != c_in || (uintptr_t)features % 16 == 0) &&
@@ -1091,8 +1010,18 @@ int spconv_forward_tc(const float *features, const float *weight, const float *p
                                residual, relu, out, st);
   }
   const bool bf = precision == BEVB200_PREC_BF16X3;
-  const int variant = tc_variant(bf);
-  float *padded = nullptr;
+  const int variant = tc_variant(bf) == 4 ? 4 : 5;
+  // stream-ordered temporaries, released on every exit path
+  struct Temps {
+    cudaStream_t st;
+    float *padded = nullptr, *packed = nullptr;
+    ~Temps() {
+      if (packed) cudaFreeAsync(packed, st);
+      if (padded) cudaFreeAsync(padded, st);
+    }
+  } tmp;
+  tmp.st = st;
+  float *&padded = tmp.padded;
   if (c_eff != c_in) {   // e.g. conv_input (Cin = 5 -> 8): zero-padded copy of the rows, padded weights
     BEVB200_CUDA(cudaMallocAsync((void **)&padded, (size_t)(n_in > 0 ? n_in : 1) * c_eff * sizeof(float), st));
     if (n_in > 0)
@@ -1109,7 +1038,7 @@ int spconv_forward_tc(const float *features, const float *weight, const float *p
   const int nbr_bytes = kvol * kTileM * 4;
   const int grid_tiles = (n_out + kTileM - 1) / kTileM;
 
-  float *packed = nullptr;
+  float *&packed = tmp.packed;
   const float *wpacked = packed_in;
   if (packed_in == nullptr) {
     BEVB200_CUDA(cudaMallocAsync((void **)&packed, spconv_packed_bytes(c_in_real, c_out, kvol, precision), st));
@@ -1128,6 +1057,8 @@ int spconv_forward_tc(const float *features, const float *weight, const float *p
       const char *e = getenv("BEVB200_SPCONV_NMERGE");
       merge_env = e ? atoi(e) : 1;
     }
+    p4.dbg = 0;
+#ifdef BEVB200_TC_PROFILE
     {
       static int dbg_env = -1;
       if (dbg_env < 0) {
@@ -1136,6 +1067,7 @@ int spconv_forward_tc(const float *features, const float *weight, const float *p
       }
       p4.dbg = dbg_env;
     }
+#endif
     p4.nmerge = (merge_env && (nsplit == 2 || bf) && c_out <= 64) ? 1 : 0;
     p4.acc_cols = p4.nmerge ? (2 * c_out < 32 ? 32 : 2 * c_out) : acc_cols;
     {
@@ -1230,8 +1162,6 @@ int spconv_forward_tc(const float *features, const float *weight, const float *p
     if (lrc) return lrc;
     ++g_launch_count;
   }
-  if (packed) BEVB200_CUDA(cudaFreeAsync(packed, st));
-  if (padded) BEVB200_CUDA(cudaFreeAsync(padded, st));
   return BEVB200_OK;
 }
 

@@ -46,14 +46,25 @@ class SparseEncoder(nn.Module):
         encoder_out_channels = self.make_encoder_layers(make_sparse_convmodule, norm_cfg,
                                                         self.base_channels, block_type=block_type)
         self.overlap_rulebooks = os.environ.get("BEVB200_RULEBOOK_STREAM", "1") != "0"
+        # eval mode, default precision: the whole encoder is one native, sync-free call (encoder_plan.py);
+        # BEVB200_ENCODER_NATIVE=0 keeps the per-conv python loop below (A/B runs, other precisions)
+        self.native_plan = os.environ.get("BEVB200_ENCODER_NATIVE", "1") != "0"
+        self._plan = None
         self.rulebook_lookahead = os.environ.get("BEVB200_RULEBOOK_LOOKAHEAD", "1") != "0"
         self.conv_out = make_sparse_convmodule(encoder_out_channels, self.output_channels,
                                                kernel_size=(1, 1, 3), stride=(1, 1, 2),
                                                norm_cfg=norm_cfg, padding=0,
                                                indice_key="spconv_down2", conv_type="SparseConv3d")
 
+    def plan(self):
+        """The native EncoderPlan of this module (built lazily), or None when a layer has no native form."""
+        if self._plan is None:
+            from . import encoder_plan
+            self._plan = encoder_plan.EncoderPlan(self) if encoder_plan.supported(self) else False
+        return self._plan or None
+
     def forward(self, voxel_features, coors, batch_size, fused=None, precision=None, out=None,
-                **kwargs):
+                num_voxels=None, **kwargs):
         """sparse_encoder.py:99-132.  voxel_features [N, C] fp32, coors [N, 4] int32
         (batch, x, y, z).  Returns spatial features [B, C*D, H, W].
 
@@ -64,6 +75,15 @@ class SparseEncoder(nn.Module):
         coors = coors.int()
         if fused is None:
             fused = not self.training and self.order == ("conv", "norm", "act")
+        if precision is None:
+            precision = sp_ops.default_precision()
+        if (fused and self.native_plan and precision == sp_ops.PREC_BF16X3 and not torch.is_grad_enabled()
+                and voxel_features.dtype == torch.float32 and self.plan() is not None):
+            # `num_voxels` (device int32[1]): only the first rows are valid -- no host round trip
+            return self.plan().forward(voxel_features.contiguous(), coors.contiguous(), batch_size,
+                                       n_voxels_dev=num_voxels, out=out, overlap_rulebooks=self.overlap_rulebooks)
+        if num_voxels is not None:
+            raise ValueError("num_voxels= needs the native plan (eval mode, bf16x3, no grad)")
         x = spconv.SparseConvTensor(voxel_features, coors, self.sparse_shape, batch_size)
         if fused:
             return self._forward_fused(x, precision, out)

@@ -25,20 +25,9 @@ def register(cls):
     return cls
 
 
-def _calculate_fan_in_and_fan_out_hwio(tensor):
-    dimensions = tensor.ndimension()
-    if dimensions < 2:
-        raise ValueError("fan in and fan out can not be computed for tensor with fewer than 2 dimensions")
-    if dimensions == 2:
-        fan_in, fan_out = tensor.size(-2), tensor.size(-1)
-    else:
-        num_input_fmaps, num_output_fmaps = tensor.size(-2), tensor.size(-1)
-        receptive_field_size = 1
-        if tensor.dim() > 2:
-            receptive_field_size = tensor[..., 0, 0].numel()
-        fan_in = num_input_fmaps * receptive_field_size
-        fan_out = num_output_fmaps * receptive_field_size
-    return fan_in, fan_out
+def _fan_in(weight):
+    """Inputs feeding one output channel of a [k..., Cin, Cout] filter (conv.py:107-112 init)."""
+    return weight[..., 0].numel()
 
 
 class SparseConvolution(SparseModule):
@@ -97,8 +86,7 @@ class SparseConvolution(SparseModule):
     def reset_parameters(self):
         init.kaiming_uniform_(self.weight, a=math.sqrt(5))
         if self.bias is not None:
-            fan_in, _ = _calculate_fan_in_and_fan_out_hwio(self.weight)
-            bound = 1 / math.sqrt(fan_in)
+            bound = 1 / math.sqrt(_fan_in(self.weight))
             init.uniform_(self.bias, -bound, bound)
 
     # -- rulebook lookup / build (conv.py:152-182) ------------------------------------------
@@ -156,10 +144,24 @@ class SparseConvolution(SparseModule):
         (scale, shift), a residual add and ReLU into the conv epilogue."""
         assert isinstance(input, SparseConvTensor)
         features = input.features
+        fused = scale is not None or shift is not None or residual is not None or relu
+        needs_grad = torch.is_grad_enabled() and (features.requires_grad or self.weight.requires_grad)
+        if fused and needs_grad:
+            # the fused epilogues are an inference path: refusing is better than silently dropping gradients
+            raise RuntimeError("fused BN / residual / ReLU epilogues do not record gradients; call the conv "
+                               "without them (or under torch.no_grad())")
         if self.conv1x1:
             features = torch.mm(input.features, self.weight.view(self.in_channels, self.out_channels))
             if self.bias is not None:
-                features += self.bias
+                features = features + self.bias
+            if scale is not None:
+                features = features * scale
+            if shift is not None:
+                features = features + shift
+            if residual is not None:
+                features = features + residual
+            if relu:
+                features = torch.relu(features)
             out_tensor = SparseConvTensor(features, input.indices, input.spatial_shape,
                                           input.batch_size)
             out_tensor.indice_dict = input.indice_dict
@@ -170,8 +172,7 @@ class SparseConvolution(SparseModule):
         if ready is not None:                       # built on the side stream: order this stream after it
             torch.cuda.current_stream(features.device).wait_event(ready)
             rb.ready = None
-        fused = scale is not None or shift is not None or residual is not None or relu
-        if fused or not torch.is_grad_enabled() or not (features.requires_grad or self.weight.requires_grad):
+        if fused or not needs_grad:
             if self.bias is not None:
                 # bias folds into the epilogue shift: (acc + b) * s + t = acc * s + (b * s + t)
                 b = self.bias.detach()

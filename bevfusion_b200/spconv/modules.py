@@ -1,92 +1,50 @@
-"""SparseModule / SparseSequential -- mirror of mmdet3d/ops/spconv/modules.py."""
-import sys
+"""Containers for sparse modules (the role of mmdet3d/ops/spconv/modules.py:77-139): a
+`SparseSequential` is a plain `nn.Sequential` whose dense members (BatchNorm1d, ReLU, ...) are applied to
+the `.features` of the SparseConvTensor that flows through it.  Same sub-module naming as
+`nn.Sequential` ("0", "1", ... or the given names), so reference state_dicts load unchanged."""
 from collections import OrderedDict
 
-import torch
 from torch import nn
 
 from .structure import SparseConvTensor
 
 
-def is_spconv_module(module):
-    return isinstance(module, SparseModule)
-
-
-def is_sparse_conv(module):
-    from .conv import SparseConvolution
-    return isinstance(module, SparseConvolution)
-
-
 class SparseModule(nn.Module):
-    """Marker base class: modules that take a SparseConvTensor (modules.py:77-81)."""
-    pass
+    """Marker base: a module whose forward takes a SparseConvTensor."""
 
 
-class SparseSequential(SparseModule):
-    """Sequential container that feeds sparse modules the tensor and dense modules its
-    `.features` (modules.py:84-139)."""
-
-    def __init__(self, *args, **kwargs):
-        super().__init__()
-        if len(args) == 1 and isinstance(args[0], OrderedDict):
-            for key, module in args[0].items():
-                self.add_module(key, module)
+class SparseSequential(nn.Sequential, SparseModule):
+    def __init__(self, *modules, **named):
+        if len(modules) == 1 and isinstance(modules[0], OrderedDict):
+            super().__init__(modules[0])
         else:
-            for idx, module in enumerate(args):
-                self.add_module(str(idx), module)
-        for name, module in kwargs.items():
-            if sys.version_info < (3, 6):
-                raise ValueError("kwargs only supported in py36+")
+            super().__init__(*modules)
+        for name, module in named.items():
             if name in self._modules:
-                raise ValueError("name exists.")
+                raise ValueError(f"duplicate sub-module name {name!r}")
             self.add_module(name, module)
-        self._sparity_dict = {}
-
-    def __getitem__(self, idx):
-        if not (-len(self) <= idx < len(self)):
-            raise IndexError("index {} is out of range".format(idx))
-        if idx < 0:
-            idx += len(self)
-        it = iter(self._modules.values())
-        for _ in range(idx):
-            next(it)
-        return next(it)
-
-    def __len__(self):
-        return len(self._modules)
-
-    @property
-    def sparity_dict(self):
-        return self._sparity_dict
 
     def add(self, module, name=None):
-        if name is None:
-            name = str(len(self._modules))
-            if name in self._modules:
-                raise KeyError("name exists")
-        self.add_module(name, module)
+        self.add_module(str(len(self)) if name is None else name, module)
 
-    def forward(self, input):
-        for k, module in self._modules.items():
-            if is_spconv_module(module):
-                assert isinstance(input, SparseConvTensor)
-                self._sparity_dict[k] = input.sparity
-                input = module(input)
+    def forward(self, x):
+        for module in self:
+            if isinstance(module, SparseModule):
+                x = module(x)
+            elif isinstance(x, SparseConvTensor):
+                if x.features.shape[0]:        # dense layers see the [N, C] feature matrix
+                    x.features = module(x.features)
             else:
-                if isinstance(input, SparseConvTensor):
-                    if input.indices.shape[0] != 0:
-                        input.features = module(input.features)
-                else:
-                    input = module(input)
-        return input
+                x = module(x)
+        return x
 
 
 class ToDense(SparseModule):
-    def forward(self, x: SparseConvTensor):
+    def forward(self, x):
         return x.dense()
 
 
 class RemoveGrid(SparseModule):
-    def forward(self, x: SparseConvTensor):
+    def forward(self, x):
         x.grid = None
         return x

@@ -90,9 +90,6 @@ def _listify(v, ndim):
     return list(v) if isinstance(v, (list, tuple)) else [v] * ndim
 
 
-_SITE_STATE = {}   # outids.data_ptr() -> (outids tensor, workspace, batch, out_shape) of strided convs
-
-
 def get_rulebook(indices, batch_size, spatial_shape, ksize=3, stride=1, padding=0, dilation=1,
                  out_padding=0, subm=False, transpose=False):
     """Build the rulebook of one conv on the device (replaces getIndicePair<3>,
@@ -120,14 +117,16 @@ def get_rulebook(indices, batch_size, spatial_shape, ksize=3, stride=1, padding=
     hs, ho, hk, hst, hp, hd = (_i32(spatial_shape), _i32(out_shape), _i32(ksize), _i32(stride),
                                _i32(padding), _i32(dilation))
     if subm:
-        st = _SITE_STATE.get(indices.data_ptr())
-        if (st is not None and st[0] is indices and st[2] == batch_size and st[3] == spatial_shape
-                and n_in > 0):
+        # (workspace, batch, out_shape, ready event) left on the tensor by the strided conv that made it
+        st = getattr(indices, "_b200_site_state", None)
+        if st is not None and st[1] == batch_size and st[2] == spatial_shape and n_in > 0:
+            if st[3] is not None:          # built on another stream: order this stream after it
+                torch.cuda.current_stream(dev).wait_event(st[3])
             # rows are the outputs of a strided conv built moments ago: reuse its bitmap + ranks
             with torch.cuda.device(dev):
                 nbr = torch.empty((kvol, n_in), dtype=torch.int32, device=dev)
                 rc = L.bevb200_rulebook_fill_subm_sorted(_C.ptr(indices), n_in, batch_size, _vp(hs), _vp(hk),
-                                                         _vp(hd), _C.ptr(nbr), _C.ptr(st[1]), st[1].numel(),
+                                                         _vp(hd), _C.ptr(nbr), _C.ptr(st[0]), st[0].numel(),
                                                          _C.current_stream(dev))
             _C.check(rc, "rulebook_fill_subm_sorted")
             return Rulebook(indices, nbr, n_in, n_in, kvol), out_shape
@@ -152,11 +151,11 @@ def get_rulebook(indices, batch_size, spatial_shape, ksize=3, stride=1, padding=
         _C.check(rc, "rulebook_fill")
     rb = Rulebook(outids, nbr, n_in, n_out, kvol)
     if not subm and n_out > 0:
-        # remember the output-site state while `outids` is alive (one entry per strided conv; the
-        # dict is pruned when it grows -- entries are only valid for the identical tensor object)
-        if len(_SITE_STATE) > 16:
-            _SITE_STATE.clear()
-        _SITE_STATE[outids.data_ptr()] = (outids, ws, batch_size, list(out_shape))
+        # the output-site bitmap + ranks live exactly as long as `outids` does: they ride on the tensor
+        # object (no module-level cache), with the event a consumer on another stream must wait for
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(dev))
+        outids._b200_site_state = (ws, batch_size, list(out_shape), ready)
     return rb, out_shape
 
 
@@ -381,8 +380,9 @@ class _SparseConvExt:
     fused_indice_conv_half = fused_indice_conv_fp32
 
     def __getattr__(self, name):
-        # 2-D / 4-D rulebooks, grid rulebooks, sparse max-pool: not used by any shipped config
-        raise NotImplementedError("sparse_conv_ext.%s is outside the hot path" % name)
+        # 2-D / 4-D rulebooks, grid rulebooks, sparse max-pool: not used by any shipped config.
+        # AttributeError (not NotImplementedError) so that hasattr() / copy / pickle probing works.
+        raise AttributeError("sparse_conv_ext.%s is outside the hot path (not implemented)" % name)
 
 
 sparse_conv_ext = _SparseConvExt()

@@ -223,10 +223,15 @@ def voxelize_mean(voxels, coors, num_points, batch_idx=0):
     return feats, coords4
 
 
-def voxelize_mean_fused(points, voxel_size, coors_range, max_points, max_voxels, batch_idx=0):
+def voxelize_mean_fused(points, voxel_size, coors_range, max_points, max_voxels, batch_idx=0, sync=True):
     """hard voxelization + per-voxel mean + (batch, x, y, z) coords in one pass over the points
     (bevfusion.py:178-195 with voxelize_reduce), never materialising the [M, max_points, F]
-    voxel tensor.  Returns (feats [M, F], coords [M, 4] int32, num_points [M] int32)."""
+    voxel tensor.  Returns (feats [M, F], coords [M, 4] int32, num_points [M] int32).
+
+    sync=False keeps the voxel count on the device (the reference returns it as a host int,
+    voxelization_cuda.cu:369-370): the tensors come back at their cap size [max_voxels, ...] together
+    with `voxel_num` (device int32[1]); rows >= voxel_num are unspecified.  SparseEncoder takes that
+    count as `num_voxels=`, so a whole LiDAR frame needs no host round trip."""
     _C.require_cuda(points, "points", torch.float32)
     n, f = points.shape
     vs, cr = _floats(voxel_size, 3), _floats(coors_range, 6)
@@ -243,6 +248,8 @@ def voxelize_mean_fused(points, voxel_size, coors_range, max_points, max_voxels,
             int(max_points), int(max_voxels), int(batch_idx), _C.ptr(feats), _C.ptr(coords4),
             _C.ptr(num), _C.ptr(voxel_num), _C.ptr(ws), ws.numel(), _C.current_stream(dev))
     _C.check(rc, "hard_voxelize_mean")
+    if not sync:
+        return feats, coords4, num, voxel_num
     m = int(voxel_num.item())
     return feats[:m], coords4[:m], num[:m]
 
@@ -257,7 +264,8 @@ def voxelize_batch(points, voxelize_module, voxelize_reduce=True):
     feats, coords, sizes = [], [], []
     hard = isinstance(voxelize_module, Voxelization) and voxelize_module.max_num_points > 0
     for k, res in enumerate(points):
-        if hard and voxelize_reduce:             # fused: no [M, P, F] intermediate
+        if hard and voxelize_reduce and res.shape[1] <= 8:   # fused: no [M, P, F] intermediate (kernel: F <= 8;
+            # wider rows, e.g. 45-dim radar points, take the generic Voxelization + mean below)
             mv = voxelize_module.max_voxels[0 if voxelize_module.training else 1]
             f, c4, n = voxelize_mean_fused(res.contiguous(), voxelize_module.voxel_size,
                                            voxelize_module.point_cloud_range,

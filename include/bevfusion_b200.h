@@ -362,6 +362,36 @@ BEVB200_API int bevb200_spconv_forward_packed(const float *features, const float
                                   const float *residual, int relu, int precision, float *out,
                                   void *stream);
 
+/* Generation-6 tensor-core path (BEVB200_PREC_BF16X3), split operand images.
+ * The tcgen05 kernel consumes a feature row as the bf16 image of its hi/lo split: per group of 16
+ * channels 32 B of bf16 hi (= rn(x)) then 32 B of bf16 lo (= rn(x - hi)); c * 4 bytes per row, c a
+ * multiple of 16.  A conv writes that image of ITS output from the epilogue (out_split), so a chain of
+ * convs (SparseEncoder) splits each row once instead of once per (row, kernel offset) visit, and
+ * bevb200_spconv_forward() -- the fp32-in / fp32-out drop-in for indice_conv_fp32 -- is
+ * split_rows + forward_split.
+ *   bevb200_spconv_split_channels(c)   channel count of the image (c rounded up to 16, <= 128; 0: none)
+ *   bevb200_spconv_split_rows          fp32 rows [n, c_in] -> image [n, split_channels(c_in) * 4 B],
+ *                                      zero padded; n_dev (nullable, device int32) caps n on the device
+ *   bevb200_spconv_pack_split_weights  weight [K, c_in, c_out] fp32 -> the kernel's shared-memory image
+ *                                      (bevb200_spconv_split_weight_bytes bytes; c_in is the REAL count)
+ *   bevb200_spconv_forward_split       features_split [n_in, c_in * 4 B] (c_in = the padded count),
+ *                                      nbr [K][nbr_stride] (rows >= n_out unused), n_out_dev (nullable):
+ *                                      device-side row count <= n_out, read by the persistent kernel --
+ *                                      no host round trip for the output count of a strided conv;
+ *                                      out (fp32 rows) and / or out_split (image) are written, epilogue
+ *                                      as bevb200_spconv_forward. */
+BEVB200_API int bevb200_spconv_split_channels(int c_in);
+BEVB200_API int bevb200_spconv_split_rows(const float *features, int n, const int32_t *n_dev, int c_in,
+                              void *split, void *stream);
+BEVB200_API size_t bevb200_spconv_split_weight_bytes(int c_in, int c_out, int kernel_volume);
+BEVB200_API int bevb200_spconv_pack_split_weights(const float *weight, int c_in, int c_out, int kernel_volume,
+                                      void *packed, void *stream);
+BEVB200_API int bevb200_spconv_forward_split(const void *features_split, const void *packed_weight,
+                                 const int32_t *nbr, long long nbr_stride, int n_in, int n_out,
+                                 const int32_t *n_out_dev, int c_in, int c_out, int kernel_volume,
+                                 const float *scale, const float *shift, const float *residual, int relu,
+                                 float *out, void *out_split, void *stream);
+
 /* Sparse convolution backward.  Replaces spconv::indiceConvBackward<float> (spconv_ops.h:363-456;
  * bound as sparse_conv_ext.indice_conv_backward_fp32):
  *     input_grad[j, :]  = sum_k out_grad[nbr_t[k, j], :] @ weight[k]^T     [n_in, c_in]
@@ -390,6 +420,57 @@ BEVB200_API int bevb200_spconv_backward(const float *features, const float *weig
 BEVB200_API int bevb200_sparse_to_dense(const float *features, const int32_t *indices, int n, int c,
                             int batch_size, const int32_t *spatial_shape_host, int z_major,
                             long long out_batch_stride, float *out, void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * SparseEncoder as one native, sync-free call (reference: the python loop of
+ * mmdet3d/models/backbones/sparse_encoder.py:99-132 over spconv/conv.py:114-223, with the
+ * BatchNorm1d / ReLU / residual modules of spconv/modules.py:127-139 and ops/sparse_block.py:94-110).
+ *
+ * A plan is a chain of convs (conv i reads the output of conv i-1): SubMConv3d or strided
+ * SparseConv3d, each followed by y = acc * scale + shift (folded eval-mode BN / bias), an optional
+ * residual add of the OUTPUT of an earlier conv (SparseBasicBlock identity) and an optional ReLU.
+ * No row count ever returns to the host: buffers are sized by caps (level 0 = max_voxels; a strided
+ * conv makes at most prod(ceil(k/s)) outputs per input row and one per output site; level_caps_host,
+ * nullable, may tighten the caps of the levels >= 1), kernels read their counts from device memory,
+ * so bevb200_encoder_forward() is a fixed sequence of ~45 launches that may be captured in a CUDA graph.
+ * BEVB200_PREC_BF16X3 arithmetic (spconv generation 6).  Channel counts: 16 / 32 / 64 / 128 (the first
+ * conv's c_in: anything <= 128).
+ *   create            host-only object; destroy() frees it (and the CUDA events it may own)
+ *   param_bytes       device bytes of the parameter buffer (packed weights, scales, shifts)
+ *   set_conv          packs weight [K, c_in, c_out] fp32 and copies scale / shift [c_out] (nullable)
+ *                     into the parameter buffer (device pointers, stream ordered)
+ *   workspace_bytes   device scratch for (max_voxels, batch_size, caps)
+ *   forward           voxel_features [max_voxels, in_channels] fp32, coors [max_voxels, 4] int32
+ *                     (b, x, y, z), n_voxels_dev (nullable device int32: valid rows <= max_voxels);
+ *                     dense_out [B, C*Z, X, Y] (out_batch_stride floats, 0 = dense) is fully written;
+ *                     status_dev int32[1 + levels]: [0] != 0 when a cap truncated a level,
+ *                     [1 + l] = rows of level l.  rulebook_stream (nullable): a second stream the
+ *                     rulebooks are built on, forked from / joined to `stream` with events. */
+typedef struct {
+  int32_t c_in, c_out;
+  int32_t ksize[3], stride[3], padding[3], dilation[3];
+  int32_t subm;          /* 1: SubMConv3d (stride 1, padding k/2 forced, spconv_ops.h:74-83) */
+  int32_t relu;
+  int32_t residual_from; /* -1, or j < i: add the output of conv j before the ReLU */
+} bevb200_encoder_conv_t;
+typedef struct bevb200_encoder bevb200_encoder_t;
+BEVB200_API int bevb200_encoder_create(int in_channels, const int32_t *sparse_shape_host,
+                           const bevb200_encoder_conv_t *convs, int n_convs, bevb200_encoder_t **out);
+BEVB200_API void bevb200_encoder_destroy(bevb200_encoder_t *enc);
+BEVB200_API size_t bevb200_encoder_param_bytes(const bevb200_encoder_t *enc);
+BEVB200_API int bevb200_encoder_num_levels(const bevb200_encoder_t *enc);
+BEVB200_API int bevb200_encoder_output_shape(const bevb200_encoder_t *enc, int32_t *shape_out, int32_t *channels_out);
+BEVB200_API int bevb200_encoder_set_conv(bevb200_encoder_t *enc, int conv, const float *weight, const float *scale,
+                             const float *shift, void *params, size_t params_bytes, void *stream);
+BEVB200_API int bevb200_encoder_level_caps(const bevb200_encoder_t *enc, int max_voxels, int batch_size,
+                               const int32_t *level_caps_host, int32_t *caps_out);
+BEVB200_API size_t bevb200_encoder_workspace_bytes(const bevb200_encoder_t *enc, int max_voxels, int batch_size,
+                                       const int32_t *level_caps_host);
+BEVB200_API int bevb200_encoder_forward(bevb200_encoder_t *enc, const void *params, const float *voxel_features,
+                            const int32_t *coors, int max_voxels, const int32_t *n_voxels_dev,
+                            int batch_size, const int32_t *level_caps_host, float *dense_out,
+                            long long out_batch_stride, int32_t *status_dev, void *workspace,
+                            size_t workspace_bytes, void *stream, void *rulebook_stream);
 
 #ifdef __cplusplus
 }

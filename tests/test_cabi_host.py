@@ -100,15 +100,20 @@ def test_size_queries_of_the_later_entry_points():
     """pure host-side size arithmetic of the C ABI (no device needed)."""
     from bevfusion_b200 import _C
     L = _C.lib()
-    # input channels the tensor-core conv runs with: <= 8 -> 8 (conv_input: 5), else next power of two
+    # input channels the TF32 tensor-core kernels run with: <= 8 -> 8 (conv_input: 5), else next power of two;
+    # BF16X3 (generation 6) takes the rows as they are: its operand-split pass pads to a multiple of 16
     for c_in, want in ((1, 8), (5, 8), (8, 8), (9, 16), (16, 16), (17, 32), (64, 64), (100, 128), (128, 128)):
-        for prec in (1, 2, 3):
+        for prec in (1, 2):
             assert L.bevb200_spconv_padded_channels(c_in, prec) == want
+        assert L.bevb200_spconv_padded_channels(c_in, 3) == c_in
         assert L.bevb200_spconv_padded_channels(c_in, 0) == c_in          # exact-fp32 path: no padding
     assert L.bevb200_spconv_padded_channels(129, 3) == 129                 # no tensor-core form: unchanged
+    for c_in, want in ((1, 16), (5, 16), (16, 16), (17, 32), (33, 64), (100, 128), (128, 128), (129, 0)):
+        assert L.bevb200_spconv_split_channels(c_in) == want
     # the packed image of a padded shape is the image of the padded channel count
-    for prec in (1, 3):
-        assert L.bevb200_spconv_packed_weight_bytes(5, 16, 27, prec) == L.bevb200_spconv_packed_weight_bytes(8, 16, 27, prec) > 0
+    assert L.bevb200_spconv_packed_weight_bytes(5, 16, 27, 1) == L.bevb200_spconv_packed_weight_bytes(8, 16, 27, 1) > 0
+    assert L.bevb200_spconv_packed_weight_bytes(5, 16, 27, 3) == L.bevb200_spconv_packed_weight_bytes(16, 16, 27, 3) > 0
+    assert L.bevb200_spconv_split_weight_bytes(5, 16, 27) == L.bevb200_spconv_packed_weight_bytes(5, 16, 27, 3)
     assert L.bevb200_spconv_packed_weight_bytes(64, 48, 27, 3) == 0        # c_out must be 16 / 32 / 64 / 128
     assert L.bevb200_spconv_packed_weight_bytes(64, 64, 28, 3) == 0        # kernel volume <= 27
     assert L.bevb200_spconv_packed_weight_bytes(128, 128, 27, 3) == 27 * 128 * 128 * 2 * 2   # bf16 hi + lo
