@@ -260,12 +260,20 @@ class BEVPoolPlan:
         _C.check(rc, "bev_pool_lift")
         return out
 
+    def lift(self, depth, ctx, out=None):
+        """lift_pool + the module output layout of __call__: depth [B, N, D, fH, fW], ctx [B, N, fH, fW, C]
+        -> [B, C*nz, nx, ny] (optionally written into `out`, e.g. the fuser's camera channels)."""
+        return self._channels_first(self.lift_pool(depth, ctx), out)
+
     def __call__(self, x, out=None):
         """pool + module output layout.  `out` (optional) is a [B, Z*C, X, Y] float32 view that is
         dense inside each batch item -- e.g. the camera channels of the fuser's concatenated
         input (fusers/conv.py:16) -- and is written in place."""
-        pooled = self.pool(x)                               # [B, Z, X, Y, C]
-        # bev_pool.py:97 permute(0,4,1,2,3).contiguous() followed by base.py:174
+        return self._channels_first(self.pool(x), out)
+
+    @staticmethod
+    def _channels_first(pooled, out=None):
+        # pooled [B, Z, X, Y, C]; bev_pool.py:97 permute(0,4,1,2,3).contiguous() followed by base.py:174
         # cat(unbind(dim=2), 1) puts channel z*C + c at [b, :, x, y]: one tiled transpose does both
         B, Z, X, Y, C = pooled.shape
         if pooled.requires_grad:

@@ -416,9 +416,9 @@ int bevb200_encoder_create(int in_channels, const int32_t *sparse_shape_host, co
     if (!cv.d.subm) {
       ELevel nl;
       for (int d = 0; d < 3; ++d) {   // ops.py:20-31
-        nl.shape[d] = (e->levels[level].shape[d] + 2 * cv.d.padding[d] - cv.d.dilation[d] * (cv.d.ksize[d] - 1) - 1) /
-                          cv.d.stride[d] + 1;
-        if (nl.shape[d] <= 0) return fail("conv output shape is empty");
+        const int num = e->levels[level].shape[d] + 2 * cv.d.padding[d] - cv.d.dilation[d] * (cv.d.ksize[d] - 1) - 1;
+        if (num < 0) return fail("conv output shape is empty");
+        nl.shape[d] = num / cv.d.stride[d] + 1;
       }
       nl.c_max = cv.d.c_out;
       e->levels.push_back(nl);

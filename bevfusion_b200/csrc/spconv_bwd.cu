@@ -6,9 +6,11 @@
 //   * input gradient  = ONE implicit-GEMM launch of the forward kernel on the transposed
 //     neighbour table (nbrT[k, j] = output row fed by input row j through offset k) with the
 //     per-offset transposed weights:  dIn[j] = sum_k dOut[nbrT[k, j]] @ W[k]^T
-//   * weight gradient = one kernel: CTA (offset k, chunk of output rows) accumulates the
-//     Cin x Cout outer-product sum of its chunk in registers and adds it to dW[k] with fp32
-//     atomics (the chunk partition is fixed; only the order of ~n_out/2048 adds per element varies).
+//   * weight gradient = two kernels, NO atomics: CTA (offset k, fixed chunk of 2048 output rows)
+//     accumulates the Cin x Cout outer-product sum of its chunk in registers and stores it as a
+//     partial; a second kernel adds the partials of every element in ascending chunk order.  The
+//     result is bit-reproducible run to run (the reference's cuBLAS GEMM per offset is too; the
+//     round-1 version with fp32 atomicAdd was not).
 #include "common.cuh"
 
 namespace bevb200 {
@@ -50,7 +52,7 @@ template <int TCI, int TCO>     // per-thread micro-tile; 256 threads cover (16*
 __global__ void __launch_bounds__(256)
     spconv_wgrad_kernel(const float *__restrict__ features, const float *__restrict__ out_grad,
                         const int32_t *__restrict__ nbr, int n_in, int n_out, int c_in, int c_out,
-                        float *__restrict__ w_grad) {
+                        float *__restrict__ partial) {   // [chunk][k][c_in][c_out]
   constexpr int BCI = 16 * TCI, BCO = 16 * TCO;
   __shared__ float fs[kWgStep][BCI + 1];
   __shared__ float gs[kWgStep][BCO + 1];
@@ -100,10 +102,20 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
         for (int b = 0; b < TCO; ++b) {
           const int ci = ci0 + ty * TCI + a, co = co0 + tx * TCO + b;
-          if (ci < c_in && co < c_out && acc[a][b] != 0.f)
-            atomicAdd(w_grad + ((long long)k * c_in + ci) * c_out + co, acc[a][b]);
+          if (ci < c_in && co < c_out)
+            partial[(((long long)blockIdx.x * gridDim.y + k) * c_in + ci) * c_out + co] = acc[a][b];
         }
     }
+  }
+}
+
+// dW[e] = sum over chunks (ascending) of partial[chunk][e]
+__global__ void spconv_wgrad_reduce_kernel(const float *__restrict__ partial, long long elems, int n_chunks,
+                                           float *__restrict__ w_grad) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < elems; e += (long long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int ch = 0; ch < n_chunks; ++ch) s += partial[(long long)ch * elems + e];
+    w_grad[e] = s;
   }
 }
 
@@ -127,9 +139,11 @@ int bevb200_rulebook_transpose(const int32_t *nbr, int kernel_volume, int n_out,
   return BEVB200_OK;
 }
 
-size_t bevb200_spconv_backward_workspace_bytes(int c_in, int c_out, int kernel_volume) {
-  if (c_in <= 0 || c_out <= 0 || kernel_volume <= 0) return 0;
-  return align_up((size_t)kernel_volume * c_in * c_out * sizeof(float));
+size_t bevb200_spconv_backward_workspace_bytes(int n_out, int c_in, int c_out, int kernel_volume) {
+  if (n_out < 0 || c_in <= 0 || c_out <= 0 || kernel_volume <= 0) return 0;
+  const size_t w = align_up((size_t)kernel_volume * c_in * c_out * sizeof(float));
+  const size_t chunks = ((size_t)n_out + kWgChunk - 1) / kWgChunk;
+  return w * (1 + (chunks ? chunks : 1));     // transposed weights + one partial dW per chunk of output rows
 }
 
 int bevb200_spconv_backward(const float *features, const float *weight, const float *out_grad,
@@ -149,7 +163,7 @@ int bevb200_spconv_backward(const float *features, const float *weight, const fl
     return BEVB200_OK;
   }
   BEVB200_REQUIRE(features && out_grad && nbr && nbr_t, "null argument");
-  if (workspace == nullptr || workspace_bytes < bevb200_spconv_backward_workspace_bytes(c_in, c_out, kernel_volume)) {
+  if (workspace == nullptr || workspace_bytes < bevb200_spconv_backward_workspace_bytes(n_out, c_in, c_out, kernel_volume)) {
     snprintf(g_last_error, sizeof(g_last_error), "spconv_backward: workspace too small");
     return BEVB200_EWORKSPACE;
   }
@@ -165,18 +179,22 @@ int bevb200_spconv_backward(const float *features, const float *weight, const fl
     rc = spconv_forward_tc(out_grad, wt, nullptr, nbr_t, n_out, n_in, c_out, c_in, kernel_volume, nullptr,
                            nullptr, nullptr, 0, precision, input_grad, st);
   if (rc) return rc;
-  // dW
-  dim3 grid((n_out + kWgChunk - 1) / kWgChunk, kernel_volume);
+  // dW: per-chunk partials, then an ordered reduction (no atomics)
+  const int n_chunks = (n_out + kWgChunk - 1) / kWgChunk;
+  float *partial = (float *)((char *)workspace + align_up(wbytes));
+  dim3 grid(n_chunks, kernel_volume);
   if (c_in >= 64 && c_out >= 64) {
     BEVB200_LAUNCH((spconv_wgrad_kernel<4, 4>), grid, 256, 0, st, features, out_grad, nbr, n_in, n_out,
-                   c_in, c_out, weight_grad);
+                   c_in, c_out, partial);
   } else if (c_in >= 32 && c_out >= 32) {
     BEVB200_LAUNCH((spconv_wgrad_kernel<2, 2>), grid, 256, 0, st, features, out_grad, nbr, n_in, n_out,
-                   c_in, c_out, weight_grad);
+                   c_in, c_out, partial);
   } else {
     BEVB200_LAUNCH((spconv_wgrad_kernel<1, 1>), grid, 256, 0, st, features, out_grad, nbr, n_in, n_out,
-                   c_in, c_out, weight_grad);
+                   c_in, c_out, partial);
   }
+  const long long elems = (long long)kernel_volume * c_in * c_out;
+  BEVB200_LAUNCH(spconv_wgrad_reduce_kernel, grid_for(elems, 256), 256, 0, st, partial, elems, n_chunks, weight_grad);
   return BEVB200_OK;
 }
 

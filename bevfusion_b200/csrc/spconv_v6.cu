@@ -56,6 +56,7 @@ struct V6Params {
   int merged;                   // 1: A_hi x [W_hi | W_lo] (Cout <= 64); 0: three products (Cout = 128)
   int nsa, nsb, b_stage_bytes;
   int tmem_cols;
+  int proxy_fence;               // tuning: fence.proxy.async before the MMAs of an item (BEVB200_V6_FENCE)
 };
 
 __device__ __forceinline__ void tc_mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
@@ -159,7 +160,7 @@ __global__ void __launch_bounds__(kV6Threads, 2) spconv_v6_kernel(const V6Params
 
   if (tid == 0) {
     for (int s = 0; s < nsa; ++s) {
-      mbar_init(a_full + 8 * s, 128);   // cp.async arrivals of the four gather warps that fill the stage
+      mbar_init(a_full + 8 * s, 4);     // one arrival per gather warp that fills the stage
       mbar_init(a_empty + 8 * s, 1);
     }
     for (int s = 0; s < nsb; ++s) {
@@ -201,6 +202,8 @@ __global__ void __launch_bounds__(kV6Threads, 2) spconv_v6_kernel(const V6Params
     uint32_t dst_off[8];                        // row (32 q + 8 m + t), swizzled chunk c ^ t
 #pragma unroll
     for (int t = 0; t < 8; ++t) dst_off[t] = (uint32_t)((q * 32 + 8 * m + t) * 128 + ((c ^ t) << 4));
+    const bool lag = nsa >= 3;   // signalling one item late needs a third stage (see the hand-off below)
+    int pend = -1;               // stage whose copies are committed but not yet signalled
     int gs = 0;             // A ring stage / phase of the first item of the current group
     uint32_t gph = 0, acc_ph = 0;
     for (int tb = t_begin; tb < t_end;) {
@@ -217,43 +220,83 @@ __global__ void __launch_bounds__(kV6Threads, 2) spconv_v6_kernel(const V6Params
       }
       // neighbour indices of one item: lane l holds the input row of output row (quarter base + l);
       // they are fetched one item ahead so that the L2 latency hides behind the stage wait
+      // (the values are NOT touched here -- not even compared -- so the loads stay in flight across the
+      // stage wait; the range check happens where they are consumed)
       auto load_idx = [&](int i, int &v0, int &v1) {
         const int kb = i >> rs, r = i & (r_cur - 1);
         const int row = (tb + r) * kV6TileM + q * 32 + lane;
         const int k0 = two_offsets ? 2 * kb : ((kb * 32) >> cin_shift);
-        v0 = (k0 < kvol && row < n_out) ? __ldg(p.nbr + (long long)k0 * nbr_stride + row) : -1;
-        if (v0 >= n_in) v0 = -1;
-        v1 = -1;
-        if (two_offsets) {
-          const int k1 = 2 * kb + 1;
-          v1 = (k1 < kvol && row < n_out) ? __ldg(p.nbr + (long long)k1 * nbr_stride + row) : -1;
-          if (v1 >= n_in) v1 = -1;
-        }
+        v0 = v1 = -1;
+        if (k0 < kvol && row < n_out) v0 = __ldg(p.nbr + (long long)k0 * nbr_stride + row);
+        if (two_offsets && 2 * kb + 1 < kvol && row < n_out)
+          v1 = __ldg(p.nbr + (long long)(2 * kb + 1) * nbr_stride + row);
       };
-      int v0 = -1, v1 = -1;
-      if (par < n_items) load_idx(par, v0, v1);
-      for (int i = par; i < n_items; i += 2) {
+      // A ring of PF index registers per lane: the indices of the warp's item j are loaded while it works on
+      // item j - PF.  (One item ahead was not enough: the L1 queue in front of the loads is full of this
+      // kernel's own cp.async traffic and ncu showed the warps parked on the index load, not on a stage.)
+      constexpr int PF = 4;
+      int v0q[PF], v1q[PF];
+#pragma unroll
+      for (int j = 0; j < PF; ++j) {
+        v0q[j] = v1q[j] = -1;
+        if (par + 2 * j < n_items) load_idx(par + 2 * j, v0q[j], v1q[j]);
+      }
+      for (int ibase = par; ibase < n_items; ibase += 2 * PF) {
+#pragma unroll
+        for (int j = 0; j < PF; ++j) {
+        const int i = ibase + 2 * j;
+        if (i >= n_items) break;
         const int kb = i >> rs;
         const int kk = kb * 32 + 4 * c;
-        int n0 = -1, n1 = -1;
-        if (i + 2 < n_items) load_idx(i + 2, n0, n1);
         unsigned long long base = fbase + (unsigned)((kk & cin_mask) << 2);
         asm volatile("" : "+l"(base));
+        // the 8 source rows of this lane's copies: all shuffles first, then all copies
+        int src[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          src[t] = __shfl_sync(0xffffffffu, v0q[j], 8 * m + t);
+          if (two_offsets) {
+            const int src1 = __shfl_sync(0xffffffffu, v1q[j], 8 * m + t);
+            src[t] = (c & 4) ? src1 : src[t];
+          }
+          if (src[t] >= n_in) src[t] = -1;
+        }
+        v0q[j] = v1q[j] = -1;
+        if (i + 2 * PF < n_items) load_idx(i + 2 * PF, v0q[j], v1q[j]);     // refill the slot
         mbar_wait(a_empty + 8 * s, ph ^ 1u);
         const uint32_t stage = a_ring + (uint32_t)s * (uint32_t)kV6AStageBytes;
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          int src = __shfl_sync(0xffffffffu, v0, 8 * m + t);
-          if (two_offsets) {
-            const int src1 = __shfl_sync(0xffffffffu, v1, 8 * m + t);
-            src = (c & 4) ? src1 : src;
+        for (int t = 0; t < 8; ++t)
+          cp_async16_row(stage + dst_off[t], base + (unsigned long long)(uint32_t)max(src[t], 0) * row_bytes, src[t]);
+        // Completion hand-off.  cp.async.mbarrier.arrive.noinc would signal from every LANE: 32 shared-memory
+        // atomics per warp and item -- ncu counted them as 43 % of the LSU's shared-memory wavefronts of this
+        // kernel.  Instead the warp commits the item as a cp.async group and signals the PREVIOUS item with ONE
+        // arrive once that group has landed (wait_group 1): by then its copies have had a whole item's time.
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (lag) {
+          if (pend >= 0) {
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_full + 8 * pend);
           }
-          cp_async16_row(stage + dst_off[t], base + (unsigned long long)(uint32_t)max(src, 0) * row_bytes, src);
+          pend = s;
+        } else {
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(a_full + 8 * s);
         }
-        cp_async_mbar_arrive_noinc(a_full + 8 * s);
-        v0 = n0; v1 = n1;
         s += 2;
         if (s >= nsa) { s -= nsa; ph ^= 1u; }
+        }
+      }
+      if (pend >= 0) {        // the last item of the group
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_full + 8 * pend);
+        pend = -1;
       }
       // ------------------------------- epilogue of the group --------------------------------
       mbar_wait(acc_full, acc_ph);
@@ -315,7 +358,7 @@ __global__ void __launch_bounds__(kV6Threads, 2) spconv_v6_kernel(const V6Params
         const bool b_done = r == r_cur - 1 && (!merged || (kb & 1) || kb == nkb - 1);
         if (b_new) mbar_wait(b_full + 8 * sb, pb);
         mbar_wait(a_full + 8 * sa, pa);
-        fence_proxy_async();
+        if (p.proxy_fence) fence_proxy_async();
         tc_fence_after();
         if (elect_one_sync()) {
           const uint32_t a_base = a_ring + (uint32_t)sa * (uint32_t)kV6AStageBytes;
@@ -534,6 +577,8 @@ int spconv_v6_forward(const void *features_split, const void *packed, const int3
   p.merged = c_out <= 64 ? 1 : 0;
   p.acc_cols = p.merged ? (2 * c_out < 32 ? 32 : 2 * c_out) : c_out;
   p.tmem_cols = 256;
+  static const int fence_env = env_int("BEVB200_V6_FENCE", 0);
+  p.proxy_fence = fence_env;
   int r = p.tmem_cols / p.acc_cols;
   if (r > 4) r = 4;
   static const int r_env = env_int("BEVB200_V6_R", 0);

@@ -15,7 +15,7 @@ small = "small" in sys.argv
 L = S.LIDAR_C3
 if small:
     rng = np.random.default_rng(0)
-    shape = [48, 40, 9]
+    shape = [48, 40, 41]
     flat = rng.choice(shape[0] * shape[1] * shape[2], size=5000, replace=False)
     coords = torch.from_numpy(np.stack([np.zeros_like(flat), flat // (shape[1] * shape[2]),
                                         (flat // shape[2]) % shape[1], flat % shape[2]], 1).astype(np.int32)).to(dev)
