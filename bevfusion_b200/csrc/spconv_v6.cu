@@ -199,9 +199,13 @@ __global__ void __launch_bounds__(kV6Threads, 2) spconv_v6_kernel(const V6Params
     const int cin_shift = p.cin_shift, cin_mask = p.c_in - 1, kvol = p.kvol, n_in = p.n_in;
     const bool two_offsets = p.c_in == 16;     // a K block then spans two kernel offsets (chunks 0-3 / 4-7)
     const long long nbr_stride = p.nbr_stride;
-    uint32_t dst_off[8];                        // row (32 q + 8 m + t), swizzled chunk c ^ t
+    // Lane (m, c) of copy instruction t writes PHYSICAL chunk c of row 32 q + 8 m + t -- the eight lanes of a row
+    // store 128 contiguous bytes in lane order -- and fetches the LOGICAL chunk c ^ t that the SWIZZLE_128B layout
+    // keeps there.  (Permuting the destination instead -- lane c writes chunk c ^ t -- costs a fifth shared-memory
+    // wavefront per instruction for every t != 0: ncu, profiles/r2_conv_v6_iterations.md.)
+    uint32_t dst_off[8];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) dst_off[t] = (uint32_t)((q * 32 + 8 * m + t) * 128 + ((c ^ t) << 4));
+    for (int t = 0; t < 8; ++t) dst_off[t] = (uint32_t)((q * 32 + 8 * m + t) * 128 + (c << 4));
     const bool lag = nsa >= 3;   // signalling one item late needs a third stage (see the hand-off below)
     int pend = -1;               // stage whose copies are committed but not yet signalled
     int gs = 0;             // A ring stage / phase of the first item of the current group
@@ -247,9 +251,6 @@ __global__ void __launch_bounds__(kV6Threads, 2) spconv_v6_kernel(const V6Params
         const int i = ibase + 2 * j;
         if (i >= n_items) break;
         const int kb = i >> rs;
-        const int kk = kb * 32 + 4 * c;
-        unsigned long long base = fbase + (unsigned)((kk & cin_mask) << 2);
-        asm volatile("" : "+l"(base));
         // the 8 source rows of this lane's copies: all shuffles first, then all copies
         int src[8];
 #pragma unroll
@@ -257,7 +258,7 @@ __global__ void __launch_bounds__(kV6Threads, 2) spconv_v6_kernel(const V6Params
           src[t] = __shfl_sync(0xffffffffu, v0q[j], 8 * m + t);
           if (two_offsets) {
             const int src1 = __shfl_sync(0xffffffffu, v1q[j], 8 * m + t);
-            src[t] = (c & 4) ? src1 : src[t];
+            src[t] = ((c ^ t) & 4) ? src1 : src[t];      // logical chunks 4-7 belong to the second offset
           }
           if (src[t] >= n_in) src[t] = -1;
         }
@@ -266,8 +267,11 @@ __global__ void __launch_bounds__(kV6Threads, 2) spconv_v6_kernel(const V6Params
         mbar_wait(a_empty + 8 * s, ph ^ 1u);
         const uint32_t stage = a_ring + (uint32_t)s * (uint32_t)kV6AStageBytes;
 #pragma unroll
-        for (int t = 0; t < 8; ++t)
+        for (int t = 0; t < 8; ++t) {
+          // byte offset of logical chunk c ^ t inside the source row
+          const unsigned long long base = fbase + (unsigned)(((kb * 32 + 4 * (c ^ t)) & cin_mask) << 2);
           cp_async16_row(stage + dst_off[t], base + (unsigned long long)(uint32_t)max(src[t], 0) * row_bytes, src[t]);
+        }
         // Completion hand-off.  cp.async.mbarrier.arrive.noinc would signal from every LANE: 32 shared-memory
         // atomics per warp and item -- ncu counted them as 43 % of the LSU's shared-memory wavefronts of this
         // kernel.  Instead the warp commits the item as a cp.async group and signals the PREVIOUS item with ONE
@@ -335,59 +339,73 @@ __global__ void __launch_bounds__(kV6Threads, 2) spconv_v6_kernel(const V6Params
     }
   } else if (warp == 8) {
     // =============================== MMA issuer ==========================================
+    // The issue loop is the serial resource of the CTA (ncu: with ~110 SASS instructions per item this warp never
+    // waited and the gather warps queued behind it), so everything per item is a running value: the shared-memory
+    // descriptors advance by constants (16 KB A stage = +1024 in 16-byte units, +2 per 32-byte K step), the
+    // accumulator address by acc_cols, and (kb, r) are loop counters instead of shifts of an item index.
     const uint32_t idesc_n = umma_idesc_bf16(kV6TileM, c_out);
     const uint32_t idesc_2n = umma_idesc_bf16(kV6TileM, 2 * c_out);
-    const int merged = p.merged;
+    const bool merged = p.merged != 0;
+    const uint64_t a_desc0 = umma_desc_sw128(a_ring), b_desc0 = umma_desc_sw128(b_ring);
+    const uint64_t b_step = (uint64_t)(p.b_stage_bytes >> 4);
+    const uint32_t acc_cols = (uint32_t)p.acc_cols;
+    uint64_t a_cur = a_desc0, b_cur = b_desc0;
     int sa = 0, sb = 0;
     uint32_t pa = 0, pb = 0, pe = 0;
     bool first_group = true;
     for (int tb = t_begin; tb < t_end;) {
       int rs = p.r_shift;
       while ((1 << rs) > t_end - tb) --rs;
-      const int r_cur = 1 << rs, n_items = nkb << rs;
+      const int r_cur = 1 << rs;
       if (!first_group) {                 // the epilogue warps have drained the accumulators
         mbar_wait(acc_empty, pe);
         pe ^= 1u;
         tc_fence_after();
       }
       first_group = false;
-      for (int i = 0; i < n_items; ++i) {
-        const int kb = i >> rs, r = i & (r_cur - 1);
+      for (int kb = 0; kb < nkb; ++kb) {
         // merged image: one weight stage = two K blocks; three-product image: one K block
-        const bool b_new = r == 0 && (!merged || (kb & 1) == 0);
-        const bool b_done = r == r_cur - 1 && (!merged || (kb & 1) || kb == nkb - 1);
+        const bool b_new = !merged || (kb & 1) == 0;
+        const bool b_last = !merged || (kb & 1) || kb == nkb - 1;
+        const bool k_last = kb == nkb - 1;
         if (b_new) mbar_wait(b_full + 8 * sb, pb);
-        mbar_wait(a_full + 8 * sa, pa);
-        if (p.proxy_fence) fence_proxy_async();
-        tc_fence_after();
-        if (elect_one_sync()) {
-          const uint32_t a_base = a_ring + (uint32_t)sa * (uint32_t)kV6AStageBytes;
-          const uint32_t bstage = b_ring + (uint32_t)sb * (uint32_t)p.b_stage_bytes;
-          const uint32_t d = tmem_base + (uint32_t)(r * p.acc_cols);
-          const uint64_t bdesc = umma_desc_sw128(bstage);
-#pragma unroll
-          for (int g = 0; g < 2; ++g) {   // the two 16-channel groups of the K block
-            const uint64_t a_hi = umma_desc_sw128(a_base + (uint32_t)(g * 64));
-            const uint64_t a_lo = umma_desc_sw128(a_base + (uint32_t)(g * 64 + 32));
-            const uint32_t acc0 = (kb == 0 && g == 0) ? 0u : 1u;
+        const uint64_t bk = b_cur + (merged ? (uint64_t)((kb & 1) * 4) : 0ull);
+        const uint32_t acc0 = kb ? 1u : 0u;
+        uint32_t d = tmem_base;
+        for (int r = 0; r < r_cur; ++r, d += acc_cols) {
+          mbar_wait(a_full + 8 * sa, pa);
+          if (p.proxy_fence) fence_proxy_async();
+          tc_fence_after();
+          if (elect_one_sync()) {
+            // A tile row: [hi g0 | lo g0 | hi g1 | lo g1], 32 B each
             if (merged) {
-              const uint64_t b = bdesc + (uint64_t)((kb & 1) * 4 + g * 2);   // 16-byte units along K
-              tc_mma_bf16_ss(d, a_hi, b, idesc_2n, acc0);    // hi*hi -> cols [0, c), hi*lo -> [c, 2c)
-              tc_mma_bf16_ss(d, a_lo, b, idesc_n, 1u);       // lo*hi -> cols [0, c)
+              tc_mma_bf16_ss(d, a_cur, bk, idesc_2n, acc0);          // hi*hi -> cols [0, c), hi*lo -> [c, 2c)
+              tc_mma_bf16_ss(d, a_cur + 2, bk, idesc_n, 1u);         // lo*hi -> cols [0, c)
+              tc_mma_bf16_ss(d, a_cur + 4, bk + 2, idesc_2n, 1u);
+              tc_mma_bf16_ss(d, a_cur + 6, bk + 2, idesc_n, 1u);
             } else {
-              const uint64_t b_hi = bdesc + (uint64_t)(g * 2), b_lo = bdesc + (uint64_t)(4 + g * 2);
-              tc_mma_bf16_ss(d, a_lo, b_hi, idesc_n, acc0);
-              tc_mma_bf16_ss(d, a_hi, b_lo, idesc_n, 1u);
-              tc_mma_bf16_ss(d, a_hi, b_hi, idesc_n, 1u);
+              // weight row: [W_hi g0 | W_hi g1 | W_lo g0 | W_lo g1]
+              tc_mma_bf16_ss(d, a_cur + 2, bk, idesc_n, acc0);       // lo*hi
+              tc_mma_bf16_ss(d, a_cur, bk + 4, idesc_n, 1u);         // hi*lo
+              tc_mma_bf16_ss(d, a_cur, bk, idesc_n, 1u);             // hi*hi
+              tc_mma_bf16_ss(d, a_cur + 6, bk + 2, idesc_n, 1u);
+              tc_mma_bf16_ss(d, a_cur + 4, bk + 6, idesc_n, 1u);
+              tc_mma_bf16_ss(d, a_cur + 4, bk + 2, idesc_n, 1u);
+            }
+            tc_commit(a_empty + 8 * sa);
+            if (r == r_cur - 1) {
+              if (b_last) tc_commit(b_empty + 8 * sb);
+              if (k_last) tc_commit(acc_full);
             }
           }
-          tc_commit(a_empty + 8 * sa);
-          if (b_done) tc_commit(b_empty + 8 * sb);
-          if (i == n_items - 1) tc_commit(acc_full);
+          __syncwarp();
+          a_cur += 1024;
+          if (++sa == nsa) { sa = 0; pa ^= 1u; a_cur = a_desc0; }
         }
-        __syncwarp();
-        if (++sa == nsa) { sa = 0; pa ^= 1u; }
-        if (b_done && ++sb == nsb) { sb = 0; pb ^= 1u; }
+        if (b_last) {
+          b_cur += b_step;
+          if (++sb == nsb) { sb = 0; pb ^= 1u; b_cur = b_desc0; }
+        }
       }
       tb += r_cur;
     }
