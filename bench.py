@@ -301,7 +301,7 @@ def graph_time_ms(device, fn, n=20):
     return ms
 
 
-def conv_kernel_times(hp, points, frames=3):
+def conv_kernel_times(hp, points, frames=3, backward=False):
     """CUDA-event time of the encoder's sparse-conv kernel launches, one by one: the native plan runs the
     convs back to back on one stream, so each conv is re-run alone here through the same C entry point
     (bevb200_spconv_forward_split) on the plan's real rulebooks.  Returns (ms per frame over the conv
@@ -328,6 +328,7 @@ def conv_kernel_times(hp, points, frames=3):
         for h in hooks:
             h.remove()
     total, per_layer = 0.0, []
+    bwd_total = [0.0]
     for (mod, inp), row in zip(convs, rows):
         rb, _ = mod._rulebook(inp)
         cin, cout, kv = mod.in_channels, mod.out_channels, rb.nbr.shape[0]
@@ -349,9 +350,22 @@ def conv_kernel_times(hp, points, frames=3):
                                                       _C.ptr(osp), _C.current_stream(dev)), "forward_split")
         ms = time_ms(run, n=frames * 3, warm=2)
         total += ms
-        per_layer.append(dict(row, us=round(ms * 1e3, 1),
-                              tflops=round(2.0 * row["pairs"] * cin * cout / (ms * 1e-3) / 1e12, 2)))
+        entry = dict(row, us=round(ms * 1e3, 1), tflops=round(2.0 * row["pairs"] * cin * cout / (ms * 1e-3) / 1e12, 2))
+        if backward:
+            # training side (spconv_ops.h:363-456): input gradient = the forward kernel on the transposed table,
+            # filter gradient = chunked outer products + ordered reduction (no atomics)
+            from bevfusion_b200.spconv import ops as sp_ops
+            nbr_t = sp_ops.transpose_nbr(rb.nbr, n_in)
+            gout = torch.randn(rb.n_out, cout, device=dev)
+            feats_f = inp.features.contiguous()
+            bms = time_ms(lambda: sp_ops.sparse_conv_backward(feats_f, w, gout, rb.nbr, nbr_t), n=3, warm=1)
+            entry["backward_us"] = round(bms * 1e3, 1)
+            bwd_total[0] += bms
+            del nbr_t, gout
+        per_layer.append(entry)
     del spconv
+    if backward:
+        return total, len(convs), per_layer, bwd_total[0]
     return total, len(convs), per_layer
 
 
@@ -516,7 +530,7 @@ def c5_leg(device, peaks):
     call_ms = time_ms(lambda: hp.plan(x), n=10)
     nbytes = hp.bev_pool_bytes()
     depth, ctx = hp.lift_inputs(seed=0, device=device)
-    lift_ms = time_ms(lambda: hp.plan.lift(depth, ctx), n=10)
+    lift_ms = graph_time_ms(device, lambda: hp.plan.lift(depth, ctx), n=10)
     del x, depth, ctx
     lid_ms = time_ms(lambda: hp._lidar(pts), n=10)
     rows, n_vox = hp.encoder_work(pts)
@@ -723,7 +737,17 @@ def run_ours(args, rank, world, local_rank):
     bwd_ms = time_ms(lambda: _PoolPerm.backward(_Ctx, og))
     bwd_bytes = 4 * 80 * t.n_intervals + 4 * 80 * t.n_total + 4 * t.n_total
     depth, ctx = hp.lift_inputs(seed=0, device=device)
-    lift_ms = time_ms(lambda: hp.plan.lift_pool(depth, ctx))
+    lift_ms = graph_time_ms(device, lambda: hp.plan.lift_pool(depth, ctx))
+    os.environ["BEVB200_LIFT_VARIANT"] = "rows"            # the round-1 kernel: one context-row gather per kept point
+    try:
+        lift_rows_ms = graph_time_ms(device, lambda: hp.plan.lift_pool(depth, ctx))
+    finally:
+        del os.environ["BEVB200_LIFT_VARIANT"]
+    t0 = time.perf_counter()
+    hp.plan._lift_cache = None
+    hp.plan.lift_pool(depth, ctx)
+    torch.cuda.synchronize()
+    lift_prepare_ms = (time.perf_counter() - t0) * 1e3 - lift_ms
     del og, depth, ctx
     # SURVEY.md section 8(f) rows (timed alone, CUDA events, median of 20):
     from bevfusion_b200 import synthetic as S_
@@ -731,14 +755,14 @@ def run_ours(args, rank, world, local_rank):
     from bevfusion_b200.voxelize import voxel_layer, voxelize_mean, voxelize_mean_fused
     from bevfusion_b200.vtransform import points_to_depth
     L_ = S_.LIDAR_C3
-    fused_vox_ms = time_ms(lambda: voxelize_mean_fused(pts, L_["voxel_size"], L_["point_cloud_range"], 10, 160000, 0, sync=False))
+    fused_vox_ms = graph_time_ms(device, lambda: voxelize_mean_fused(pts, L_["voxel_size"], L_["point_cloud_range"], 10, 160000, 0, sync=False))
     unfused_vox_ms = time_ms(lambda: voxelize_mean(*hp_voxelize(pts, L_), 0))
     dcoors = torch.zeros(pts.shape[0], 3, dtype=torch.int32, device=device)
     voxel_layer.dynamic_voxelize(pts, dcoors, L_["voxel_size"], L_["point_cloud_range"], 3)
     scatter_ms = time_ms(lambda: dynamic_scatter(pts, dcoors, "mean"))
     M_ = S_.lidar_camera_matrices(6, (256, 704), batch=1)
     margs = (M_["lidar2image"].to(device), M_["img_aug_matrix"].to(device), M_["lidar_aug_matrix"].to(device), (256, 704))
-    depth_ms = time_ms(lambda: points_to_depth([pts], *margs))
+    depth_ms = graph_time_ms(device, lambda: points_to_depth([pts], *margs))
     next_rows = {"voxelize_mean_fused_ms": round(fused_vox_ms, 4), "voxelize_then_mean_ms": round(unfused_vox_ms, 4),
                  "dynamic_scatter_mean_ms": round(scatter_ms, 4), "lidar_depth_images_6x256x704_ms": round(depth_ms, 4),
                  "points": int(pts.shape[0]),
@@ -775,7 +799,7 @@ def run_ours(args, rank, world, local_rank):
                     note="latency bound: ~9 MB of algorithmic traffic in ~8 dependent launches")
     # dominant kernel of the step: the tcgen05 sparse conv (21 launches per frame); each launch is timed alone
     # with CUDA events, achieved = useful FLOPs of those launches / their summed time (burst peak: timed alone)
-    conv_ms, conv_launches, per_layer = conv_kernel_times(hp, pts)
+    conv_ms, conv_launches, per_layer, conv_bwd_ms = conv_kernel_times(hp, pts, backward=True)
     conv_tflops = flops / (conv_ms * 1e-3) / 1e12
     roof_conv = dict(kernel="spconv_v6_kernel (tcgen05 SS-form implicit-GEMM sparse conv, BF16x3, pre-split operands; %d launches per frame)" % conv_launches,
                      bound="tensor", achieved=round(conv_tflops, 3), peak=peaks["bf16_tflops"], unit="TFLOP/s",
@@ -836,8 +860,17 @@ def run_ours(args, rank, world, local_rank):
         "bev_pool_extra": {"backward_ms": round(bwd_ms, 4), "backward_GBs": round(bwd_bytes / (bwd_ms * 1e-3) / 1e9, 1),
                            "backward_frac_of_hbm_peak": round(bwd_bytes / (bwd_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
                            "fwd_plus_bwd_ms": round(pool_ms + bwd_ms, 4), "fused_lift_pool_ms": round(lift_ms, 4),
-                           "note": "backward = bevpool_bwd_kernel through perm (660 MB algorithmic); fused lift+pool reads "
-                                   "depth (8 MB) + L2-resident ctx (5.4 MB) instead of the 638 MB lifted volume"},
+                           "fused_lift_pool_round1_row_kernel_ms": round(lift_rows_ms, 4),
+                           "fused_lift_tables_build_ms_per_calibration": round(lift_prepare_ms, 3),
+                           "note": "backward = bevpool_bwd_kernel through perm (660 MB algorithmic); fused lift+pool (column "
+                                   "kernels): depth (8 MB) + ctx (5.4 MB) read once, per-segment rows written and read once, "
+                                   "instead of one 320-byte context-row gather per kept point; graph-replay times"},
+        "training": {"bev_pool_fwd_ms": round(pool_ms, 4), "bev_pool_bwd_ms": round(bwd_ms, 4),
+                     "spconv_fwd_ms_21_convs": round(conv_ms, 4), "spconv_bwd_ms_21_convs": round(conv_bwd_ms, 4),
+                     "note": "BASELINE config #2 asks for fwd+bwd: bev_pool backward = write stream through perm; spconv "
+                             "backward per conv = input gradient (forward kernel on the transposed neighbour table, "
+                             "bf16x3) + filter gradient (SIMT outer products, per-chunk partials + ordered reduction: "
+                             "bit-reproducible); each launch timed alone"},
         "next_rows": next_rows,
         "roofline": dominant, "roofline_bev_pool": roof_pool, "roofline_bev_pool_op": roof_pool_op,
         "roofline_encoder": roof_enc, "roofline_voxelize": roof_vox,

@@ -12,6 +12,7 @@ per calibration on the device and then pools straight from the un-sorted, un-fil
 volume.  All compute happens in libbevfusion_b200.so; CPU tensors are rejected.
 """
 import ctypes
+import os
 
 import torch
 
@@ -237,6 +238,35 @@ class BEVPoolPlan:
         c = x.shape[-1]
         return _PoolPerm.apply(x.reshape(-1, c).contiguous(), self.tables)
 
+    def _lift_tables(self, cameras, D, fH, fW):
+        """(column, depth bin, cell) segment tables of the column lift, built once per plan on first use."""
+        key = (cameras, D, fH, fW)
+        cached = getattr(self, "_lift_cache", None)
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        t = self.tables
+        dev = t.perm.device
+        L = _C.lib()
+        with torch.cuda.device(dev):
+            i32 = dict(dtype=torch.int32, device=dev)
+            col_begin = torch.empty(cameras * fW + 1, **i32)
+            seg_key = torch.empty(max(t.n_kept, 1), dtype=torch.int64, device=dev)
+            seg_mask = torch.empty(max(t.n_kept, 1), dtype=torch.int64, device=dev)
+            seg_slot = torch.empty(max(t.n_kept, 1), **i32)
+            ival_begin = torch.empty(t.n_intervals + 1, **i32)
+            n_seg = torch.zeros(1, **i32)
+            ws = _ws(L.bevb200_bev_pool_lift_prepare_workspace_bytes(t.n_kept), dev)
+            rc = L.bevb200_bev_pool_lift_prepare(_C.ptr(t.perm), _C.ptr(t.starts), t.n_kept, t.n_intervals, cameras, D,
+                                                 fH, fW, _C.ptr(col_begin), _C.ptr(seg_key), _C.ptr(seg_mask),
+                                                 _C.ptr(seg_slot), _C.ptr(ival_begin), _C.ptr(n_seg), _C.ptr(ws),
+                                                 ws.numel(), _C.current_stream(dev))
+            _C.check(rc, "bev_pool_lift_prepare")
+            n = int(n_seg.item())
+            tables = (col_begin, seg_key[:max(n, 1)].clone(), seg_mask[:max(n, 1)].clone(), seg_slot[:max(n, 1)].clone(),
+                      ival_begin, n)
+        self._lift_cache = (key, tables)
+        return tables
+
     def lift_pool(self, depth, ctx):
         """Fused LSS lift + pool (inference): `depth` [B, N, D, fH, fW] softmax volume and `ctx`
         [B, N, fH, fW, C] channels-last context features -> raw op output [B, nz, nx, ny, C], equal
@@ -250,6 +280,21 @@ class BEVPoolPlan:
         t = self.tables
         assert depth.numel() == t.n_total
         Bq, Dq, Hq, Wq = t.dims
+        if fH <= 64 and os.environ.get("BEVB200_LIFT_VARIANT", "columns") != "rows":
+            # column formulation: context rows and depth values of an image column are staged once in shared
+            # memory and every (column, depth bin, cell) segment is evaluated from there
+            col_begin, seg_key, seg_mask, seg_slot, ival_begin, n_seg = self._lift_tables(B * N, D, fH, fW)
+            L = _C.lib()
+            with torch.cuda.device(depth.device):
+                out = torch.empty((Bq, Dq, Hq, Wq, c), dtype=torch.float32, device=depth.device)
+                ws = _ws(L.bevb200_bev_pool_lift_columns_workspace_bytes(n_seg, t.n_intervals, c), depth.device)
+                rc = L.bevb200_bev_pool_lift_columns(
+                    Bq, Dq, Hq, Wq, t.n_kept, c, t.n_intervals, _C.ptr(depth), _C.ptr(ctx), B * N, D, fH, fW,
+                    _C.ptr(t.geom), _C.ptr(t.starts), _C.ptr(col_begin), _C.ptr(seg_key), _C.ptr(seg_mask),
+                    _C.ptr(seg_slot), _C.ptr(ival_begin), n_seg, _C.ptr(out), _C.ptr(ws), ws.numel(),
+                    _C.current_stream(depth.device))
+            _C.check(rc, "bev_pool_lift_columns")
+            return out
         with torch.cuda.device(depth.device):
             out = torch.empty((Bq, Dq, Hq, Wq, c), dtype=torch.float32, device=depth.device)
             ws = _ws(_C.lib().bevb200_bev_pool_workspace_bytes(t.n_kept, c), depth.device)

@@ -37,7 +37,7 @@ namespace bevb200 {
 constexpr int kV6Threads = 10 * 32;
 constexpr int kV6TileM = 128;
 constexpr int kV6AStageBytes = kV6TileM * 128;   // 128 rows x 128 B
-constexpr int kV6MaxA = 8, kV6MaxB = 4;
+constexpr int kV6MaxA = 12, kV6MaxB = 4;
 
 struct V6Params {
   const uint8_t *fsplit;        // split image of the input rows, c_in * 4 bytes per row
@@ -57,6 +57,7 @@ struct V6Params {
   int nsa, nsb, b_stage_bytes;
   int tmem_cols;
   int proxy_fence;               // tuning: fence.proxy.async before the MMAs of an item (BEVB200_V6_FENCE)
+  int lag;                       // tuning: signal an item when the next one is issued (BEVB200_V6_LAG, default 1)
 };
 
 __device__ __forceinline__ void tc_mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
@@ -206,7 +207,7 @@ __global__ void __launch_bounds__(kV6Threads, 2) spconv_v6_kernel(const V6Params
     uint32_t dst_off[8];
 #pragma unroll
     for (int t = 0; t < 8; ++t) dst_off[t] = (uint32_t)((q * 32 + 8 * m + t) * 128 + (c << 4));
-    const bool lag = nsa >= 3;   // signalling one item late needs a third stage (see the hand-off below)
+    const bool lag = nsa >= 3 && p.lag;   // signalling one item late needs a third stage (see the hand-off below)
     int pend = -1;               // stage whose copies are committed but not yet signalled
     int gs = 0;             // A ring stage / phase of the first item of the current group
     uint32_t gph = 0, acc_ph = 0;
@@ -339,73 +340,63 @@ __global__ void __launch_bounds__(kV6Threads, 2) spconv_v6_kernel(const V6Params
     }
   } else if (warp == 8) {
     // =============================== MMA issuer ==========================================
-    // The issue loop is the serial resource of the CTA (ncu: with ~110 SASS instructions per item this warp never
-    // waited and the gather warps queued behind it), so everything per item is a running value: the shared-memory
-    // descriptors advance by constants (16 KB A stage = +1024 in 16-byte units, +2 per 32-byte K step), the
-    // accumulator address by acc_cols, and (kb, r) are loop counters instead of shifts of an item index.
+    // (A leaner issue loop -- running descriptors, ~50 instead of ~110 SASS instructions per item -- was measured
+    // SLOWER at C = 64 / 128 (2.85 vs 2.69 ms for the 21 convs, profiles/r2_conv_v6_iterations.md): this warp is
+    // not what paces the CTA once the shared-memory pipe is ~85 % busy, and its denser barrier polling costs
+    // shared-memory wavefronts.)
     const uint32_t idesc_n = umma_idesc_bf16(kV6TileM, c_out);
     const uint32_t idesc_2n = umma_idesc_bf16(kV6TileM, 2 * c_out);
-    const bool merged = p.merged != 0;
-    const uint64_t a_desc0 = umma_desc_sw128(a_ring), b_desc0 = umma_desc_sw128(b_ring);
-    const uint64_t b_step = (uint64_t)(p.b_stage_bytes >> 4);
-    const uint32_t acc_cols = (uint32_t)p.acc_cols;
-    uint64_t a_cur = a_desc0, b_cur = b_desc0;
+    const int merged = p.merged;
     int sa = 0, sb = 0;
     uint32_t pa = 0, pb = 0, pe = 0;
     bool first_group = true;
     for (int tb = t_begin; tb < t_end;) {
       int rs = p.r_shift;
       while ((1 << rs) > t_end - tb) --rs;
-      const int r_cur = 1 << rs;
+      const int r_cur = 1 << rs, n_items = nkb << rs;
       if (!first_group) {                 // the epilogue warps have drained the accumulators
         mbar_wait(acc_empty, pe);
         pe ^= 1u;
         tc_fence_after();
       }
       first_group = false;
-      for (int kb = 0; kb < nkb; ++kb) {
+      for (int i = 0; i < n_items; ++i) {
+        const int kb = i >> rs, r = i & (r_cur - 1);
         // merged image: one weight stage = two K blocks; three-product image: one K block
-        const bool b_new = !merged || (kb & 1) == 0;
-        const bool b_last = !merged || (kb & 1) || kb == nkb - 1;
-        const bool k_last = kb == nkb - 1;
+        const bool b_new = r == 0 && (!merged || (kb & 1) == 0);
+        const bool b_done = r == r_cur - 1 && (!merged || (kb & 1) || kb == nkb - 1);
         if (b_new) mbar_wait(b_full + 8 * sb, pb);
-        const uint64_t bk = b_cur + (merged ? (uint64_t)((kb & 1) * 4) : 0ull);
-        const uint32_t acc0 = kb ? 1u : 0u;
-        uint32_t d = tmem_base;
-        for (int r = 0; r < r_cur; ++r, d += acc_cols) {
-          mbar_wait(a_full + 8 * sa, pa);
-          if (p.proxy_fence) fence_proxy_async();
-          tc_fence_after();
-          if (elect_one_sync()) {
-            // A tile row: [hi g0 | lo g0 | hi g1 | lo g1], 32 B each
+        mbar_wait(a_full + 8 * sa, pa);
+        if (p.proxy_fence) fence_proxy_async();
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const uint32_t a_base = a_ring + (uint32_t)sa * (uint32_t)kV6AStageBytes;
+          const uint32_t bstage = b_ring + (uint32_t)sb * (uint32_t)p.b_stage_bytes;
+          const uint32_t d = tmem_base + (uint32_t)(r * p.acc_cols);
+          const uint64_t bdesc = umma_desc_sw128(bstage);
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {   // the two 16-channel groups of the K block
+            const uint64_t a_hi = umma_desc_sw128(a_base + (uint32_t)(g * 64));
+            const uint64_t a_lo = umma_desc_sw128(a_base + (uint32_t)(g * 64 + 32));
+            const uint32_t acc0 = (kb == 0 && g == 0) ? 0u : 1u;
             if (merged) {
-              tc_mma_bf16_ss(d, a_cur, bk, idesc_2n, acc0);          // hi*hi -> cols [0, c), hi*lo -> [c, 2c)
-              tc_mma_bf16_ss(d, a_cur + 2, bk, idesc_n, 1u);         // lo*hi -> cols [0, c)
-              tc_mma_bf16_ss(d, a_cur + 4, bk + 2, idesc_2n, 1u);
-              tc_mma_bf16_ss(d, a_cur + 6, bk + 2, idesc_n, 1u);
+              const uint64_t b = bdesc + (uint64_t)((kb & 1) * 4 + g * 2);   // 16-byte units along K
+              tc_mma_bf16_ss(d, a_hi, b, idesc_2n, acc0);    // hi*hi -> cols [0, c), hi*lo -> [c, 2c)
+              tc_mma_bf16_ss(d, a_lo, b, idesc_n, 1u);       // lo*hi -> cols [0, c)
             } else {
-              // weight row: [W_hi g0 | W_hi g1 | W_lo g0 | W_lo g1]
-              tc_mma_bf16_ss(d, a_cur + 2, bk, idesc_n, acc0);       // lo*hi
-              tc_mma_bf16_ss(d, a_cur, bk + 4, idesc_n, 1u);         // hi*lo
-              tc_mma_bf16_ss(d, a_cur, bk, idesc_n, 1u);             // hi*hi
-              tc_mma_bf16_ss(d, a_cur + 6, bk + 2, idesc_n, 1u);
-              tc_mma_bf16_ss(d, a_cur + 4, bk + 6, idesc_n, 1u);
-              tc_mma_bf16_ss(d, a_cur + 4, bk + 2, idesc_n, 1u);
-            }
-            tc_commit(a_empty + 8 * sa);
-            if (r == r_cur - 1) {
-              if (b_last) tc_commit(b_empty + 8 * sb);
-              if (k_last) tc_commit(acc_full);
+              const uint64_t b_hi = bdesc + (uint64_t)(g * 2), b_lo = bdesc + (uint64_t)(4 + g * 2);
+              tc_mma_bf16_ss(d, a_lo, b_hi, idesc_n, acc0);
+              tc_mma_bf16_ss(d, a_hi, b_lo, idesc_n, 1u);
+              tc_mma_bf16_ss(d, a_hi, b_hi, idesc_n, 1u);
             }
           }
-          __syncwarp();
-          a_cur += 1024;
-          if (++sa == nsa) { sa = 0; pa ^= 1u; a_cur = a_desc0; }
+          tc_commit(a_empty + 8 * sa);
+          if (b_done) tc_commit(b_empty + 8 * sb);
+          if (i == n_items - 1) tc_commit(acc_full);
         }
-        if (b_last) {
-          b_cur += b_step;
-          if (++sb == nsb) { sb = 0; pb ^= 1u; b_cur = b_desc0; }
-        }
+        __syncwarp();
+        if (++sa == nsa) { sa = 0; pa ^= 1u; }
+        if (b_done && ++sb == nsb) { sb = 0; pb ^= 1u; }
       }
       tb += r_cur;
     }
@@ -594,9 +585,15 @@ int spconv_v6_forward(const void *features_split, const void *packed, const int3
   while ((1 << p.cin_shift) < c_in) ++p.cin_shift;
   p.merged = c_out <= 64 ? 1 : 0;
   p.acc_cols = p.merged ? (2 * c_out < 32 ? 32 : 2 * c_out) : c_out;
-  p.tmem_cols = 256;
+  // tuning: BEVB200_V6_CTAS=1 runs ONE persistent CTA per SM (all 512 TMEM columns, ~225 KB of shared memory:
+  // more A stages in flight per SM because only one weight ring is resident) instead of two
+  static const int ctas_env = env_int("BEVB200_V6_CTAS", 2);
+  const int ctas = ctas_env == 1 ? 1 : 2;
+  p.tmem_cols = ctas == 1 ? 512 : 256;
   static const int fence_env = env_int("BEVB200_V6_FENCE", 0);
   p.proxy_fence = fence_env;
+  static const int lag_env = env_int("BEVB200_V6_LAG", 1);
+  p.lag = lag_env;
   int r = p.tmem_cols / p.acc_cols;
   if (r > 4) r = 4;
   static const int r_env = env_int("BEVB200_V6_R", 0);
@@ -605,7 +602,7 @@ int spconv_v6_forward(const void *features_split, const void *packed, const int3
   while ((2 << p.r_shift) <= r) ++p.r_shift;
   p.b_stage_bytes = p.merged ? 2 * c_out * 128 : c_out * 128;
   // per CTA (two per SM): 1 KB alignment slack + weight ring + A ring
-  const int budget = 111 * 1024 - 1024;
+  const int budget = (ctas == 1 ? 225 : 111) * 1024 - 1024;
   static const int nsb_env = env_int("BEVB200_V6_NSB", 0);
   p.nsb = nsb_env >= 2 && nsb_env <= kV6MaxB ? nsb_env : ((!p.merged || p.b_stage_bytes <= 8192) ? 3 : 2);
   p.nsa = (budget - p.nsb * p.b_stage_bytes) / kV6AStageBytes;
@@ -615,7 +612,7 @@ int spconv_v6_forward(const void *features_split, const void *packed, const int3
   BEVB200_REQUIRE(p.nsa >= 2, "shared memory budget: no room for two A stages");
   const size_t smem = (size_t)p.nsb * p.b_stage_bytes + (size_t)p.nsa * kV6AStageBytes + 1024;
   const int n_tiles = (n_out + kV6TileM - 1) / kV6TileM;
-  int grid = 2 * kNumSMs;
+  int grid = ctas * kNumSMs;
   if (grid > n_tiles) grid = n_tiles;
   BEVB200_CUDA(cudaFuncSetAttribute(spconv_v6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   BEVB200_LAUNCH(spconv_v6_kernel, grid, kV6Threads, smem, st, p);

@@ -122,6 +122,38 @@ BEVB200_API int bevb200_bev_pool_lift(int b, int d, int h, int w, int n, int c, 
                           const int32_t *interval_starts, const int32_t *interval_lengths,
                           float *out, void *workspace, size_t workspace_bytes, void *stream);
 
+/* Column formulation of the fused lift + pool (round 2).  The BEV grid collapses z, so the fH pixels of one image
+ * column (cam, w) at one depth bin (almost) always fall into one cell: the kept points are grouped into SEGMENTS
+ * (column, depth bin, cell) with a bit mask over the pixel row h (feature_h <= 64), a segment's value
+ *     T[seg, :] = sum_{h in mask} fp32(depth[cam, d, h, w] * ctx[cam, h, w, :])
+ * is evaluated from ONE shared-memory copy of the column's context rows and depth values, and a cell is the sum of
+ * its segments in a fixed order.  Nothing is assumed about the cameras (tilt or the z filter only add segments).
+ * Reads depth + ctx once (13.4 MB at C2) instead of one 320-byte context row per kept point (588 MB through L2).
+ *   bevb200_bev_pool_lift_prepare   per calibration, from the tables of bevb200_bev_pool_prepare_*: perm [n_kept]
+ *       (sorted -> original index over [cameras, depth_bins, feature_h, feature_w], cameras = B*N) and
+ *       interval_starts.  Outputs (device): col_begin int32[cameras*feature_w + 1], seg_key / seg_mask
+ *       uint64[n_kept] (first n_segments entries valid; key = ((column*depth_bins + d) << 32) | interval),
+ *       seg_slot int32[n_kept], interval_slot_begin int32[n_intervals + 1], n_segments int32[1].
+ *       Synchronises the stream once (it needs the segment count).
+ *   bevb200_bev_pool_lift_columns   per frame: depth [cameras, depth_bins, feature_h, feature_w] fp32,
+ *       ctx [cameras, feature_h, feature_w, c] fp32 -> out [b, d, h, w, c] (fully written).  n_segments as read
+ *       back from the prepare call; workspace: bevb200_bev_pool_lift_columns_workspace_bytes(). */
+BEVB200_API size_t bevb200_bev_pool_lift_prepare_workspace_bytes(int n_kept);
+BEVB200_API int bevb200_bev_pool_lift_prepare(const int32_t *perm, const int32_t *interval_starts, int n_kept,
+                                  int n_intervals, int cameras, int depth_bins, int feature_h, int feature_w,
+                                  int32_t *col_begin, uint64_t *seg_key, uint64_t *seg_mask, int32_t *seg_slot,
+                                  int32_t *interval_slot_begin, int32_t *n_segments, void *workspace,
+                                  size_t workspace_bytes, void *stream);
+BEVB200_API size_t bevb200_bev_pool_lift_columns_workspace_bytes(int n_segments, int n_intervals, int c);
+BEVB200_API int bevb200_bev_pool_lift_columns(int b, int d, int h, int w, int n, int c, int n_intervals,
+                                  const float *depth, const float *ctx, int cameras, int depth_bins,
+                                  int feature_h, int feature_w, const int32_t *geom_feats,
+                                  const int32_t *interval_starts, const int32_t *col_begin,
+                                  const uint64_t *seg_key, const uint64_t *seg_mask, const int32_t *seg_slot,
+                                  const int32_t *interval_slot_begin, int n_segments, float *out,
+                                  void *workspace, size_t workspace_bytes, void *stream);
+
+
 /* bev_pool precompute.  Replaces, on device and in one call, the index glue of
  * BaseTransform.bev_pool (mmdet3d/models/vtransforms/base.py:149-169: quantise, batch
  * index, bounds mask), bev_pool() (ops/bev_pool/bev_pool.py:87-94: rank, argsort,
