@@ -134,13 +134,56 @@ __global__ void __launch_bounds__(256)
     const int d = e / g.fh, h = e - d * g.fh;
     dep_s[e] = __ldg(depth + ((long long)(cam * g.depth_bins + d) * g.fh + h) * g.fw + w);
   }
+  int *full_slot = reinterpret_cast<int *>(dep_s + g.depth_bins * g.fh);   // [D]: slot of the bin's all-pixels segment
+  for (int d = threadIdx.x; d < g.depth_bins; d += blockDim.x) full_slot[d] = -1;
   __syncthreads();
+  const unsigned long long full_mask = g.fh >= 64 ? ~0ull : ((1ull << g.fh) - 1ull);
+  for (int s = s0 + threadIdx.x; s < s1; s += blockDim.x)
+    if (seg_mask[s] == full_mask) full_slot[(int)((seg_key[s] >> 32) % (unsigned long long)g.depth_bins)] = slot[s];
+  __syncthreads();
+  // Dense path (the common case: every pixel of the column at a depth bin falls into ONE cell): the column is a
+  // [D x fh] . [fh x C] product.  A thread owns 4 depth bins x one float4 of channels and walks h once: 5 shared-
+  // memory loads per 16 multiply-adds instead of 2 per 4 plus the mask arithmetic of the general path below (the
+  // first version of this kernel ran every segment through that path: 121 us, issue bound).
+  const int n_dt = (g.depth_bins + 3) / 4;
+  for (int task = threadIdx.x; task < n_dt * Q; task += blockDim.x) {
+    const int q = task % Q, d0 = (task / Q) * 4;
+    int sl[4];
+    bool any = false;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      sl[j] = d0 + j < g.depth_bins ? full_slot[d0 + j] : -1;
+      any |= sl[j] >= 0;
+    }
+    if (!any) continue;
+    float4 acc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float *dv = dep_s + d0 * g.fh;
+    const int dstep = g.fh;
+    for (int h = 0; h < g.fh; ++h) {
+      const float4 c4 = ctx_s[h * Q + q];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float wgt = d0 + j < g.depth_bins ? dv[j * dstep + h] : 0.f;
+        // same arithmetic as lifting first: the product is rounded to fp32, then added
+        acc[j].x += __fmul_rn(wgt, c4.x); acc[j].y += __fmul_rn(wgt, c4.y);
+        acc[j].z += __fmul_rn(wgt, c4.z); acc[j].w += __fmul_rn(wgt, c4.w);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (sl[j] >= 0) partial[(long long)sl[j] * Q + q] = acc[j];
+  }
+  // General path: segments that cover only some pixels of the column (tilted cameras, the z filter, a column that
+  // straddles a cell boundary)
   constexpr int kGroup = Q <= 4 ? 4 : (Q <= 8 ? 8 : (Q <= 16 ? 16 : (Q <= 32 ? 32 : 64)));   // threads per segment
   const int grp = threadIdx.x / kGroup, q = threadIdx.x % kGroup, ngrp = blockDim.x / kGroup;
   if (q >= Q) return;
   for (int s = s0 + grp; s < s1; s += ngrp) {
-    const int d = (int)((seg_key[s] >> 32) % (unsigned long long)g.depth_bins);
     unsigned long long m = seg_mask[s];
+    if (m == full_mask) continue;
+    const int d = (int)((seg_key[s] >> 32) % (unsigned long long)g.depth_bins);
     const float *dv = dep_s + d * g.fh;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     while (m) {
@@ -148,7 +191,6 @@ __global__ void __launch_bounds__(256)
       m &= m - 1;
       const float wgt = dv[h];
       const float4 c4 = ctx_s[h * Q + q];
-      // same arithmetic as lifting first: the product is rounded to fp32, then added
       acc.x += __fmul_rn(wgt, c4.x); acc.y += __fmul_rn(wgt, c4.y); acc.z += __fmul_rn(wgt, c4.z); acc.w += __fmul_rn(wgt, c4.w);
     }
     partial[(long long)slot[s] * Q + q] = acc;
@@ -349,7 +391,8 @@ int bevb200_bev_pool_lift_columns(int b, int d, int h, int w, int n, int c, int 
   LiftGeom g{depth_bins, feature_h, feature_w, cameras * feature_w};
   BEVB200_LAUNCH(lift_interval_cells_kernel, grid_for(n_intervals, 256), 256, 0, st, geom_feats, interval_starts, n,
                  n_intervals, dm, cells);
-  const size_t smem = (size_t)feature_h * c * sizeof(float) + (size_t)depth_bins * feature_h * sizeof(float);
+  const size_t smem = (size_t)feature_h * c * sizeof(float) + (size_t)depth_bins * feature_h * sizeof(float) +
+                      (size_t)depth_bins * sizeof(int);
   BEVB200_REQUIRE(smem <= 200 * 1024, "image column does not fit in shared memory");
   const int total_cells = b * d * h * w;
 #define LIFT_LAUNCH(Q)                                                                                               \

@@ -57,7 +57,8 @@ struct V6Params {
   int nsa, nsb, b_stage_bytes;
   int tmem_cols;
   int proxy_fence;               // tuning: fence.proxy.async before the MMAs of an item (BEVB200_V6_FENCE)
-  int lag;                       // tuning: signal an item when the next one is issued (BEVB200_V6_LAG, default 1)
+  int lag;                       // tuning: signal an item this many of the warp's items later (BEVB200_V6_LAG: 0 / 1 / 2)
+  int gfence;                    // tuning: fence.proxy.async in the gather warps before the arrive (BEVB200_V6_GFENCE)
 };
 
 __device__ __forceinline__ void tc_mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
@@ -207,8 +208,10 @@ __global__ void __launch_bounds__(kV6Threads, 2) spconv_v6_kernel(const V6Params
     uint32_t dst_off[8];
 #pragma unroll
     for (int t = 0; t < 8; ++t) dst_off[t] = (uint32_t)((q * 32 + 8 * m + t) * 128 + (c << 4));
-    const bool lag = nsa >= 3 && p.lag;   // signalling one item late needs a third stage (see the hand-off below)
-    int pend = -1;               // stage whose copies are committed but not yet signalled
+    // an item is signalled `lag` of this warp's items later (see the hand-off below): that needs spare stages
+    const int lag = (p.lag >= 2 && nsa >= 6) ? 2 : ((p.lag >= 1 && nsa >= 3) ? 1 : 0);
+    const bool gfence = p.gfence != 0;
+    int pend = -1, pend0 = -1;   // stages whose copies are committed but not yet signalled (newest, older)
     int gs = 0;             // A ring stage / phase of the first item of the current group
     uint32_t gph = 0, acc_ph = 0;
     for (int tb = t_begin; tb < t_end;) {
@@ -278,17 +281,26 @@ __global__ void __launch_bounds__(kV6Threads, 2) spconv_v6_kernel(const V6Params
         // kernel.  Instead the warp commits the item as a cp.async group and signals the PREVIOUS item with ONE
         // arrive once that group has landed (wait_group 1): by then its copies have had a whole item's time.
         asm volatile("cp.async.commit_group;" ::: "memory");
-        if (lag) {
+        if (lag == 2) {
+          if (pend0 >= 0) {
+            asm volatile("cp.async.wait_group 2;" ::: "memory");
+            if (gfence) fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_full + 8 * pend0);
+          }
+          pend0 = pend;
+          pend = s;
+        } else if (lag == 1) {
           if (pend >= 0) {
             asm volatile("cp.async.wait_group 1;" ::: "memory");
-            fence_proxy_async();
+            if (gfence) fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(a_full + 8 * pend);
           }
           pend = s;
         } else {
           asm volatile("cp.async.wait_group 0;" ::: "memory");
-          fence_proxy_async();
+          if (gfence) fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(a_full + 8 * s);
         }
@@ -296,12 +308,15 @@ __global__ void __launch_bounds__(kV6Threads, 2) spconv_v6_kernel(const V6Params
         if (s >= nsa) { s -= nsa; ph ^= 1u; }
         }
       }
-      if (pend >= 0) {        // the last item of the group
+      if (pend0 >= 0 || pend >= 0) {        // the last item(s) of the group
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-        fence_proxy_async();
+        if (gfence) fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive(a_full + 8 * pend);
-        pend = -1;
+        if (lane == 0) {
+          if (pend0 >= 0) mbar_arrive(a_full + 8 * pend0);
+          if (pend >= 0) mbar_arrive(a_full + 8 * pend);
+        }
+        pend0 = pend = -1;
       }
       // ------------------------------- epilogue of the group --------------------------------
       mbar_wait(acc_full, acc_ph);
@@ -594,6 +609,8 @@ int spconv_v6_forward(const void *features_split, const void *packed, const int3
   p.proxy_fence = fence_env;
   static const int lag_env = env_int("BEVB200_V6_LAG", 1);
   p.lag = lag_env;
+  static const int gfence_env = env_int("BEVB200_V6_GFENCE", 1);
+  p.gfence = gfence_env;
   int r = p.tmem_cols / p.acc_cols;
   if (r > 4) r = 4;
   static const int r_env = env_int("BEVB200_V6_R", 0);

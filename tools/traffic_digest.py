@@ -1,5 +1,5 @@
 """ncu launch-list CSV (tools/frame_once.py under ncu) -> profiles/r2_launches.md + profiles/r2_traffic.json.
-Takes the last third of the launches (= the last of 3 frames)."""
+Takes the last frame of the list (from its pool_interval_cells_kernel launch to the end)."""
 import csv, json, subprocess, sys
 from collections import OrderedDict
 
@@ -22,8 +22,10 @@ for r in rows[1:]:
         mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
         d[name] = val * mult
 launches = list(recs.values())
-per = len(launches) // frames
-last = launches[-per:]
+# one frame = from its first launch (the pooling plan's interval-cell kernel) to the end of the list
+starts = [i for i, d in enumerate(launches) if "pool_interval_cells_kernel" in d["name"]]
+last = launches[starts[-1]:]
+per = len(last)
 groups = OrderedDict()
 for d in last:
     n = d["name"].split("(")[0].replace("void ", "").replace("bevb200::", "")
