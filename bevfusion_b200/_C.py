@@ -35,6 +35,8 @@ _SIGNATURES = {
     "bevb200_bev_pool_prepare_workspace_bytes": (c_size_t, [c_int]),
     "bevb200_bev_pool_prepare_geom": (c_int, [_P, c_int, c_int, _P, _P, _P, c_int] + [_P] * 7
                                       + [c_size_t, _P]),
+    "bevb200_bev_pool_prepare_cameras": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_int] + [_P] * 8
+                                         + [c_size_t, _P]),
     "bevb200_bev_pool_prepare_coords": (c_int, [_P] + [c_int] * 5 + [_P] * 7 + [c_size_t, _P]),
     "bevb200_hard_voxelize_workspace_bytes": (c_size_t, [c_int, c_int]),
     "bevb200_hard_voxelize": (c_int, [_P, c_int, c_int, _P, _P, c_int, c_int] + [_P] * 5

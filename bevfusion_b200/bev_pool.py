@@ -171,6 +171,45 @@ def prepare_from_geometry(geom_xyz, dx, bx, nx, B):
                                   ws.numel(), _C.current_stream(g.device)))
 
 
+def prepare_from_cameras(frustum, camera2lidar_rots, camera2lidar_trans, intrins, post_rots, post_trans, dx, bx, nx,
+                         extra_rots=None, extra_trans=None, return_geometry=False):
+    """get_geometry (base.py:92-135) + quantise / filter / rank / sort / intervals in one library call: the
+    [B, N, D, fH, fW, 3] geometry tensor is not materialised.  frustum [D, fH, fW, 3] from create_frustum; the
+    calibration tensors are the reference's ([B, N, 3, 3] / [B, N, 3]; extra_* [B, 3, 3] / [B, 3]), on the GPU.
+    The 3x3 inverses and the rots @ inv(intrins) product are computed with torch exactly as the reference does."""
+    _C.require_cuda(frustum, "frustum", torch.float32)
+    dev = frustum.device
+    B, N = camera2lidar_trans.shape[:2]
+    f32 = dict(dtype=torch.float32, device=dev)
+    inv_post = torch.inverse(post_rots.to(**f32))
+    combine = camera2lidar_rots.to(**f32).matmul(torch.inverse(intrins.to(**f32)))
+    cam = torch.cat([inv_post.reshape(B * N, 9), post_trans.to(**f32).reshape(B * N, 3), combine.reshape(B * N, 9),
+                     camera2lidar_trans.to(**f32).reshape(B * N, 3)], 1).contiguous()
+    extra = None
+    if extra_rots is not None or extra_trans is not None:
+        er = extra_rots.to(**f32) if extra_rots is not None else torch.eye(3, **f32).repeat(B, 1, 1)
+        et = extra_trans.to(**f32) if extra_trans is not None else torch.zeros(B, 3, **f32)
+        extra = torch.cat([er.reshape(B, 9), et.reshape(B, 3)], 1).contiguous()
+    fr = frustum.reshape(-1, 3).contiguous()
+    n_fr = fr.shape[0]
+    n_total = n_fr * B * N
+    lower = (bx.float().cpu() - dx.float().cpu() / 2.0)
+    lower_h = _C.host_array(ctypes.c_float, [float(v) for v in lower])
+    dx_h = _C.host_array(ctypes.c_float, [float(v) for v in dx.float().cpu()])
+    nx_h = _C.host_array(ctypes.c_int32, [int(v) for v in nx])
+    dims = (int(B), int(nx[2]), int(nx[0]), int(nx[1]))
+    with torch.cuda.device(dev):
+        geom = torch.empty((n_total, 3), **f32) if return_geometry else None
+        tables = _finish_tables(n_total, dev, dims, lambda r, p, gm, s, l, c, ws:
+                                _C.lib().bevb200_bev_pool_prepare_cameras(
+                                    _C.ptr(fr), n_fr, B * N, N, _C.ptr(cam), _C.ptr(extra),
+                                    ctypes.cast(lower_h, ctypes.c_void_p), ctypes.cast(dx_h, ctypes.c_void_p),
+                                    ctypes.cast(nx_h, ctypes.c_void_p), int(B), _C.ptr(geom), _C.ptr(r), _C.ptr(p),
+                                    _C.ptr(gm), _C.ptr(s), _C.ptr(l), _C.ptr(c), _C.ptr(ws), ws.numel(),
+                                    _C.current_stream(dev)))
+    return (tables, geom) if return_geometry else tables
+
+
 class _PoolPerm(torch.autograd.Function):
     """out[b, d, h, w, :] = sum of the rows of x (ORIGINAL order) that fall into the cell."""
 
@@ -232,6 +271,18 @@ class BEVPoolPlan:
         self.dx, self.bx, self.nx = gen_dx_bx(xbound, ybound, zbound)
         self.B = geom.shape[0]
         self.tables = prepare_from_geometry(geom.contiguous(), self.dx, self.bx, self.nx, self.B)
+
+    @classmethod
+    def from_cameras(cls, frustum, camera2lidar_rots, camera2lidar_trans, intrins, post_rots, post_trans,
+                     xbound, ybound, zbound, extra_rots=None, extra_trans=None):
+        """Plan straight from the calibration: get_geometry (base.py:92-135) runs inside the plan build, the
+        96 MB geometry tensor is never written (what a per-sample camera2lidar needs every frame)."""
+        self = cls.__new__(cls)
+        self.dx, self.bx, self.nx = gen_dx_bx(xbound, ybound, zbound)
+        self.B = int(camera2lidar_trans.shape[0])
+        self.tables = prepare_from_cameras(frustum, camera2lidar_rots, camera2lidar_trans, intrins, post_rots,
+                                           post_trans, self.dx, self.bx, self.nx, extra_rots, extra_trans)
+        return self
 
     def pool(self, x):
         """[B, N, D, H, W, C] (or [N', C]) -> raw op output [B, nz, nx, ny, C]."""

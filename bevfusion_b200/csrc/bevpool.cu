@@ -897,29 +897,73 @@ struct QuantParams {
   int B, n_per_batch;
 };
 
-// keys[i] = rank of point i, or `dropped_key` (one past the largest rank) when filtered out
+// rank of a lidar-frame point, or `dropped_key` (one past the largest rank) when filtered out
+__device__ __forceinline__ uint32_t pool_rank_of_xyz(const float xyz[3], int i, const QuantParams &p, uint32_t dropped_key) {
+  // base.py:149: ((geom - (bx - dx/2)) / dx).long()  -- fp32 sub, fp32 IEEE div, trunc to 0
+  long long idx[3];
+  bool kept = true;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    float v = __fdiv_rn(__fsub_rn(xyz[k], p.lower[k]), p.dx[k]);
+    long long q = (long long)v;  // cvt.rzi.s64.f32 (NaN -> 0x8000.. : dropped below)
+    idx[k] = q;
+    kept = kept && q >= 0 && q < p.nx[k] && (v == v);
+  }
+  if (!kept) return dropped_key;
+  int b = i / p.n_per_batch;
+  // bev_pool.py:87-92 with (B, D, H, W) = (B, nz, nx, ny): x*(W*D*B) + y*(D*B) + z*B + b
+  long long W = p.nx[1], D = p.nx[2], Bn = p.B;
+  return (uint32_t)(idx[0] * (W * D * Bn) + idx[1] * (D * Bn) + idx[2] * Bn + b);
+}
+
+// keys[i] = rank of point i, or `dropped_key`
 __global__ void pool_rank_from_geom_kernel(const float *__restrict__ geom, int n, QuantParams p,
                                            uint32_t dropped_key, uint32_t *__restrict__ keys,
                                            uint32_t *__restrict__ vals) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    // base.py:149: ((geom - (bx - dx/2)) / dx).long()  -- fp32 sub, fp32 IEEE div, trunc to 0
-    long long idx[3];
-    bool kept = true;
+    const float xyz[3] = {geom[3ll * i], geom[3ll * i + 1], geom[3ll * i + 2]};
+    keys[i] = pool_rank_of_xyz(xyz, i, p, dropped_key);
+    vals[i] = (uint32_t)i;
+  }
+}
+
+// BaseTransform.get_geometry (base.py:92-135) fused into the rank pass: the 96 MB [B, N, D, fH, fW, 3] tensor of
+// lidar-frame frustum points is never written.  Explicit fp32, no FMA contraction, products summed left to right:
+//   p = f - post_trans;  q = inv(post_rot) . p;  u = (q.x * q.z, q.y * q.z, q.z);  v = (R . inv(K)) . u + t
+//   [v = extra_R . v] [v += extra_t]
+// cam[c] = {inv(post_rot) 9, post_trans 3, R.inv(K) 9, t 3} (24 floats, the 3x3 inverses / product come from the
+// caller exactly as the reference computes them with torch); extra[b] = {extra_R 9, extra_t 3} or null.
+__device__ __forceinline__ void mat3_vec(const float *m, const float in[3], float out[3]) {
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      float v = __fdiv_rn(__fsub_rn(geom[3ll * i + k], p.lower[k]), p.dx[k]);
-      long long q = (long long)v;  // cvt.rzi.s64.f32 (NaN -> 0x8000.. : dropped below)
-      idx[k] = q;
-      kept = kept && q >= 0 && q < p.nx[k] && (v == v);
+  for (int r = 0; r < 3; ++r)
+    out[r] = __fadd_rn(__fadd_rn(__fmul_rn(m[3 * r], in[0]), __fmul_rn(m[3 * r + 1], in[1])), __fmul_rn(m[3 * r + 2], in[2]));
+}
+__global__ void pool_rank_from_cameras_kernel(const float *__restrict__ frustum, int n_frustum, int cams_per_batch,
+                                              const float *__restrict__ cam, const float *__restrict__ extra, int n,
+                                              QuantParams p, uint32_t dropped_key, uint32_t *__restrict__ keys,
+                                              uint32_t *__restrict__ vals, float *__restrict__ geom_out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int c = i / n_frustum, f = i - c * n_frustum;
+    const float *m = cam + 24 * c;
+    float a[3], q[3], v[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) a[k] = __fsub_rn(__ldg(frustum + 3 * f + k), __ldg(m + 9 + k));
+    mat3_vec(m, a, q);
+    const float u[3] = {__fmul_rn(q[0], q[2]), __fmul_rn(q[1], q[2]), q[2]};
+    mat3_vec(m + 12, u, v);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) v[k] = __fadd_rn(v[k], __ldg(m + 21 + k));
+    if (extra) {
+      const float *e = extra + 12 * (c / cams_per_batch);
+      float w[3];
+      mat3_vec(e, v, w);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) v[k] = __fadd_rn(w[k], __ldg(e + 9 + k));
     }
-    uint32_t key = dropped_key;
-    if (kept) {
-      int b = i / p.n_per_batch;
-      // bev_pool.py:87-92 with (B, D, H, W) = (B, nz, nx, ny): x*(W*D*B) + y*(D*B) + z*B + b
-      long long W = p.nx[1], D = p.nx[2], Bn = p.B;
-      key = (uint32_t)(idx[0] * (W * D * Bn) + idx[1] * (D * Bn) + idx[2] * Bn + b);
+    if (geom_out) {
+      geom_out[3ll * i] = v[0]; geom_out[3ll * i + 1] = v[1]; geom_out[3ll * i + 2] = v[2];
     }
-    keys[i] = key;
+    keys[i] = pool_rank_of_xyz(v, i, p, dropped_key);
     vals[i] = (uint32_t)i;
   }
 }
@@ -1155,6 +1199,42 @@ int bevb200_bev_pool_prepare_geom(const float *geom_xyz, int n_total, int n_per_
   // (B, D, H, W) = (B, nz, nx, ny)
   return prepare_finish(w, n_total, total_cells, B, nx_host[2], nx_host[1], ranks_sorted, perm,
                         geom_sorted, interval_starts, interval_lengths, counts, st);
+}
+
+int bevb200_bev_pool_prepare_cameras(const float *frustum, int n_frustum, int cameras, int cams_per_batch,
+                                     const float *cam_params, const float *extra_params, const float *lower_host,
+                                     const float *dx_host, const int32_t *nx_host, int B, float *geom_out,
+                                     int32_t *ranks_sorted, int32_t *perm, int32_t *geom_sorted,
+                                     int32_t *interval_starts, int32_t *interval_lengths, int32_t *counts,
+                                     void *workspace, size_t workspace_bytes, void *stream) {
+  BEVB200_REQUIRE(n_frustum > 0 && cameras > 0 && cams_per_batch > 0 && B > 0 && cameras == B * cams_per_batch, "bad sizes");
+  BEVB200_REQUIRE((long long)n_frustum * cameras < (1ll << 31), "too many frustum points");
+  BEVB200_REQUIRE(frustum && cam_params && lower_host && dx_host && nx_host && counts, "null argument");
+  const int n_total = n_frustum * cameras;
+  long long total_cells = (long long)nx_host[0] * nx_host[1] * nx_host[2] * B;
+  BEVB200_REQUIRE(nx_host[0] > 0 && nx_host[1] > 0 && nx_host[2] > 0, "bad grid");
+  BEVB200_REQUIRE(total_cells < 0xfffffff0ll, "grid too large for 32-bit ranks");
+  BEVB200_REQUIRE(ranks_sorted && perm && geom_sorted && interval_starts && interval_lengths, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  PrepareWs w;
+  size_t need = prepare_layout(n_total, workspace, workspace_bytes, &w);
+  if (workspace == nullptr || workspace_bytes < need) {
+    snprintf(g_last_error, sizeof(g_last_error), "bev_pool_prepare: workspace too small (%zu < %zu)",
+             workspace_bytes, need);
+    return BEVB200_EWORKSPACE;
+  }
+  QuantParams p;
+  for (int k = 0; k < 3; ++k) {
+    p.lower[k] = lower_host[k];
+    p.dx[k] = dx_host[k];
+    p.nx[k] = nx_host[k];
+  }
+  p.B = B;
+  p.n_per_batch = n_frustum * cams_per_batch;
+  BEVB200_LAUNCH(pool_rank_from_cameras_kernel, grid_for(n_total, 256), 256, 0, st, frustum, n_frustum, cams_per_batch,
+                 cam_params, extra_params, n_total, p, (uint32_t)total_cells, w.keys_a, w.vals_a, geom_out);
+  return prepare_finish(w, n_total, total_cells, B, nx_host[2], nx_host[1], ranks_sorted, perm, geom_sorted,
+                        interval_starts, interval_lengths, counts, st);
 }
 
 int bevb200_bev_pool_prepare_coords(const int64_t *coords, int n, int B, int D, int H, int W,

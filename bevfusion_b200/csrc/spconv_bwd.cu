@@ -109,6 +109,68 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Round-2 filter-gradient kernel for the encoder's channel counts (16 / 32 / 64 / 128 on both sides): ONE pass over
+// the chunk's rows for the whole Cin x Cout tile (the generic kernel above re-reads the rows once per 64 x 64 block and
+// synchronises every 16 rows).  256 threads as a 16 x 16 grid, thread tile TCI x TCO = (Cin/16) x (Cout/16); 32 rows
+// of features (gathered through nbr) and of out-grad are staged per step; rows without a neighbour are staged as zeros.
+constexpr int kWg2Step = 32;
+template <int TCI, int TCO>
+__global__ void __launch_bounds__(256)
+    spconv_wgrad2_kernel(const float *__restrict__ features, const float *__restrict__ out_grad,
+                         const int32_t *__restrict__ nbr, int n_in, int n_out, float *__restrict__ partial) {
+  constexpr int CI = 16 * TCI, CO = 16 * TCO;
+  __shared__ __align__(16) float fs[kWg2Step][CI];
+  __shared__ __align__(16) float gs[kWg2Step][CO];
+  __shared__ int js[kWg2Step];
+  const int k = blockIdx.y;
+  const int o_begin = blockIdx.x * kWgChunk, o_end = min(n_out, o_begin + kWgChunk);
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  float acc[TCI][TCO];
+#pragma unroll
+  for (int a = 0; a < TCI; ++a)
+#pragma unroll
+    for (int b = 0; b < TCO; ++b) acc[a][b] = 0.f;
+  for (int o0 = o_begin; o0 < o_end; o0 += kWg2Step) {
+    if (tid < kWg2Step) {
+      const int o = o0 + tid;
+      const int j = o < o_end ? __ldg(nbr + (long long)k * n_out + o) : -1;
+      js[tid] = (j >= 0 && j < n_in) ? j : -1;
+    }
+    __syncthreads();
+    for (int e = tid; e < kWg2Step * (CI / 4); e += 256) {
+      const int r = e / (CI / 4), c4 = e % (CI / 4), j = js[r];
+      const float4 v = j >= 0 ? __ldg(reinterpret_cast<const float4 *>(features + (long long)j * CI) + c4)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4 *>(&fs[r][4 * c4]) = v;
+    }
+    for (int e = tid; e < kWg2Step * (CO / 4); e += 256) {
+      const int r = e / (CO / 4), c4 = e % (CO / 4);
+      const float4 v = js[r] >= 0 ? __ldg(reinterpret_cast<const float4 *>(out_grad + (long long)(o0 + r) * CO) + c4)
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4 *>(&gs[r][4 * c4]) = v;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int r = 0; r < kWg2Step; ++r) {
+      float fa[TCI], gb[TCO];
+#pragma unroll
+      for (int a = 0; a < TCI; ++a) fa[a] = fs[r][ty * TCI + a];
+#pragma unroll
+      for (int b = 0; b < TCO; ++b) gb[b] = gs[r][tx * TCO + b];
+#pragma unroll
+      for (int a = 0; a < TCI; ++a)
+#pragma unroll
+        for (int b = 0; b < TCO; ++b) acc[a][b] = fmaf(fa[a], gb[b], acc[a][b]);
+    }
+    __syncthreads();
+  }
+  float *dst = partial + ((long long)blockIdx.x * gridDim.y + k) * CI * CO;
+#pragma unroll
+  for (int a = 0; a < TCI; ++a)
+#pragma unroll
+    for (int b = 0; b < TCO; ++b) dst[(ty * TCI + a) * CO + tx * TCO + b] = acc[a][b];
+}
+
 // dW[e] = sum over chunks (ascending) of partial[chunk][e]
 __global__ void spconv_wgrad_reduce_kernel(const float *__restrict__ partial, long long elems, int n_chunks,
                                            float *__restrict__ w_grad) {
@@ -183,7 +245,28 @@ int bevb200_spconv_backward(const float *features, const float *weight, const fl
   const int n_chunks = (n_out + kWgChunk - 1) / kWgChunk;
   float *partial = (float *)((char *)workspace + align_up(wbytes));
   dim3 grid(n_chunks, kernel_volume);
-  if (c_in >= 64 && c_out >= 64) {
+  auto pow16 = [](int c) { return c == 16 || c == 32 || c == 64 || c == 128; };
+  const bool aligned = (uintptr_t)features % 16 == 0 && (uintptr_t)out_grad % 16 == 0;
+#define WG2(TI, TO)                                                                                            \
+  BEVB200_LAUNCH((spconv_wgrad2_kernel<TI, TO>), grid, 256, 0, st, features, out_grad, nbr, n_in, n_out, partial)
+  if (pow16(c_in) && pow16(c_out) && aligned) {
+    const int key = (c_in / 16) * 16 + c_out / 16;
+    switch (key) {
+      case 1 * 16 + 1: WG2(1, 1); break;
+      case 1 * 16 + 2: WG2(1, 2); break;
+      case 2 * 16 + 1: WG2(2, 1); break;
+      case 2 * 16 + 2: WG2(2, 2); break;
+      case 2 * 16 + 4: WG2(2, 4); break;
+      case 4 * 16 + 2: WG2(4, 2); break;
+      case 4 * 16 + 4: WG2(4, 4); break;
+      case 4 * 16 + 8: WG2(4, 8); break;
+      case 8 * 16 + 4: WG2(8, 4); break;
+      case 8 * 16 + 8: WG2(8, 8); break;
+      default:
+        BEVB200_LAUNCH((spconv_wgrad_kernel<2, 2>), grid, 256, 0, st, features, out_grad, nbr, n_in, n_out, c_in,
+                       c_out, partial);
+    }
+  } else if (c_in >= 64 && c_out >= 64) {
     BEVB200_LAUNCH((spconv_wgrad_kernel<4, 4>), grid, 256, 0, st, features, out_grad, nbr, n_in, n_out,
                    c_in, c_out, partial);
   } else if (c_in >= 32 && c_out >= 32) {
@@ -193,6 +276,7 @@ int bevb200_spconv_backward(const float *features, const float *weight, const fl
     BEVB200_LAUNCH((spconv_wgrad_kernel<1, 1>), grid, 256, 0, st, features, out_grad, nbr, n_in, n_out,
                    c_in, c_out, partial);
   }
+#undef WG2
   const long long elems = (long long)kernel_volume * c_in * c_out;
   BEVB200_LAUNCH(spconv_wgrad_reduce_kernel, grid_for(elems, 256), 256, 0, st, partial, elems, n_chunks, weight_grad);
   return BEVB200_OK;

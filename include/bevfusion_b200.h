@@ -183,6 +183,22 @@ BEVB200_API int bevb200_bev_pool_prepare_geom(const float *geom_xyz, int n_total
 /* Same, starting from already quantised int64 coords [n, 4] = (x, y, z, b) as handed to
  * bev_pool() (bev_pool.py:84).  Rows outside [0,H)x[0,W)x[0,D)x[0,B) are dropped
  * (the reference would write out of bounds for them). */
+/* bevb200_bev_pool_prepare_geom with BaseTransform.get_geometry (mmdet3d/models/vtransforms/base.py:92-135) fused in:
+ * the lidar-frame frustum points are computed inside the rank pass and the 96 MB [B, N, D, fH, fW, 3] tensor is never
+ * written (geom_out, nullable, receives it for checks).  Explicit fp32 arithmetic, products summed left to right:
+ *   p = frustum - post_trans;  q = inv(post_rot) p;  u = (q.x q.z, q.y q.z, q.z);  v = (R inv(K)) u + t;
+ *   optionally v = extra_R v + extra_t (the lidar augmentation, per batch item).
+ * frustum [n_frustum, 3] = (u, v, d) of create_frustum (base.py:66-89); cam_params [cameras, 24] =
+ * {inv(post_rot) 9, post_trans 3, camera2lidar_rot . inv(intrinsics) 9, camera2lidar_trans 3} -- the 3x3 inverses and
+ * the product are the caller's (torch, as the reference computes them); extra_params [B, 12] or NULL; cameras = B *
+ * cams_per_batch.  Not bit-identical to torch's batched matmul (whose summation order is unspecified): a frustum point
+ * within an ulp of a cell boundary can land in the neighbouring cell. */
+BEVB200_API int bevb200_bev_pool_prepare_cameras(const float *frustum, int n_frustum, int cameras, int cams_per_batch,
+                                     const float *cam_params, const float *extra_params,
+                                     const float *lower_host, const float *dx_host, const int32_t *nx_host, int B,
+                                     float *geom_out, int32_t *ranks_sorted, int32_t *perm, int32_t *geom_sorted,
+                                     int32_t *interval_starts, int32_t *interval_lengths, int32_t *counts,
+                                     void *workspace, size_t workspace_bytes, void *stream);
 BEVB200_API int bevb200_bev_pool_prepare_coords(const int64_t *coords, int n, int B, int D, int H, int W,
                                     int32_t *ranks_sorted, int32_t *perm,
                                     int32_t *geom_sorted, int32_t *interval_starts,

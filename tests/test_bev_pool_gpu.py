@@ -270,6 +270,50 @@ def test_fused_lift_pool_arbitrary_geometry(cuda, batch):
     assert n_seg > 0.5 * plan.tables.n_kept                                    # most jittered points sit alone in their segment
 
 
+@pytest.mark.parametrize("cfg_name,batch", [("tiny", 2), ("C2", 1)])
+def test_plan_from_cameras_matches_torch_geometry(cuda, cfg_name, batch):
+    """get_geometry fused into the plan build (explicit fp32, fixed summation order) against torch's get_geometry
+    followed by the plan build: the geometry agrees to fp32 rounding, and the tables are identical except for the
+    handful of frustum points that sit within rounding of a cell boundary (each off by one cell)."""
+    from bevfusion_b200 import synthetic as S
+    from bevfusion_b200.bev_pool import BEVPoolPlan, gen_dx_bx, prepare_from_cameras
+    from bevfusion_b200.vtransform import create_frustum, get_geometry
+    cfg = S.CONFIGS[cfg_name]
+    rig = {k: v.to(cuda) for k, v in S.camera_rig(cfg["n_cam"], cfg["image_size"], batch).items()}
+    extra_r = extra_t = None
+    if batch > 1:                                           # a lidar augmentation per sample
+        M = S.lidar_camera_matrices(cfg["n_cam"], cfg["image_size"], batch)["lidar_aug_matrix"].to(cuda)
+        extra_r, extra_t = M[:, :3, :3].contiguous(), M[:, :3, 3].contiguous()
+    frustum = create_frustum(cfg["image_size"], cfg["feature_size"], cfg["dbound"]).to(cuda)
+    geom = get_geometry(frustum, rig["camera2lidar_rots"], rig["camera2lidar_trans"], rig["intrins"],
+                        rig["post_rots"], rig["post_trans"], extra_r, extra_t).contiguous()
+    ref = BEVPoolPlan(geom, cfg["xbound"], cfg["ybound"], cfg["zbound"])
+    dx, bx, nx = gen_dx_bx(cfg["xbound"], cfg["ybound"], cfg["zbound"])
+    tabs, g2 = prepare_from_cameras(frustum, rig["camera2lidar_rots"], rig["camera2lidar_trans"], rig["intrins"],
+                                    rig["post_rots"], rig["post_trans"], dx, bx, nx, extra_r, extra_t,
+                                    return_geometry=True)
+    g1 = geom.reshape(-1, 3)
+    assert float((g1 - g2).abs().max()) <= 2e-5 * float(g1.abs().max())
+    n = g1.shape[0]
+    rank_ref = torch.full((n,), -1, dtype=torch.int64, device=cuda)
+    rank_ref[ref.tables.perm[:ref.tables.n_kept].long()] = ref.tables.ranks[:ref.tables.n_kept].long()
+    rank_new = torch.full((n,), -1, dtype=torch.int64, device=cuda)
+    rank_new[tabs.perm[:tabs.n_kept].long()] = tabs.ranks[:tabs.n_kept].long()
+    differ = rank_ref != rank_new
+    assert float(differ.float().mean()) <= 2e-4                 # boundary points only
+    # every differing point is within rounding of a cell boundary in at least one axis
+    if bool(differ.any()):
+        lower = (bx - dx / 2.0).to(cuda)
+        frac = ((g1[differ] - lower) / dx.to(cuda))
+        dist = (frac - frac.round()).abs().min(dim=1).values
+        assert float(dist.max()) <= 1e-3
+    plan = BEVPoolPlan.from_cameras(frustum, rig["camera2lidar_rots"], rig["camera2lidar_trans"], rig["intrins"],
+                                    rig["post_rots"], rig["post_trans"], cfg["xbound"], cfg["ybound"], cfg["zbound"],
+                                    extra_r, extra_t)
+    assert plan.tables.n_kept == tabs.n_kept and bool(torch.equal(plan.tables.perm, tabs.perm))
+    assert abs(plan.tables.n_kept - ref.tables.n_kept) <= max(4, int(2e-4 * n))
+
+
 def test_stress_c5_properties(cuda):
     """BASELINE config C5 (6 cam 512x1408 -> 64x176 features, D=200, C=80, 256x256 BEV:
     N' = 13.5 M rows, x = 4.3 GB): size-independent properties of the plan path at full size."""

@@ -327,6 +327,36 @@ def test_native_plan_device_side_count_and_caps(cuda):
         assert bool(torch.equal(plan.forward(feats, coors, B), want)) and not plan.overflowed()
 
 
+def test_native_plan_edge_cases(cuda):
+    """zero valid rows (device-side count 0), a batch with an empty sample in the middle, and rows whose
+    coordinates lie outside the grid (ignored like the per-conv path ignores them)."""
+    shape, B = [96, 96, 41], 3
+    m = make_encoder(cuda, shape, seed=8)
+    rng = np.random.default_rng(9)
+    idx = random_sparse(4000, [96, 96, 40], B, seed=12)
+    idx = idx[idx[:, 0] != 1]                                           # sample 1 is empty
+    # far outside the grid / batch (rows one step outside would still reach border outputs of a strided conv in the
+    # reference's scatter formulation -- neither implementation validates coordinates)
+    bad = np.array([[0, -7, 5, 5], [2, 300, 0, 0], [0, 3, 3, 90], [3, 1, 1, 1]], np.int32)
+    coors = torch.from_numpy(np.concatenate([idx, bad])).to(cuda)
+    feats = torch.from_numpy(rng.standard_normal((coors.shape[0], 5)).astype(np.float32)).to(cuda)
+    with torch.no_grad():
+        native = m(feats, coors, B)
+        m.native_plan = False
+        loop = m(feats, coors, B, fused=True, precision=3)
+        m.native_plan = True
+    assert float((native - loop).abs().max()) <= 2e-5 * float(loop.abs().max())
+    assert not bool(native[1].any())                                    # the empty sample stays empty
+    with torch.no_grad():
+        zero = torch.zeros(1, dtype=torch.int32, device=cuda)
+        none = m(feats, coors, B, num_voxels=zero)
+    assert not bool(none.any())
+    assert m.plan().status.cpu().numpy()[1:].tolist() == [0] * 5
+    with torch.no_grad():                                               # and n = 0 rows at all
+        e = m(feats[:0], coors[:0], B)
+    assert tuple(e.shape) == (B, 256, 12, 12) and not bool(e.any())
+
+
 def test_native_plan_cuda_graph(cuda):
     """the encoder forward has no host synchronisation: it can be captured once and replayed on new
     voxel features / coordinates / counts written into the same buffers."""
