@@ -27,6 +27,13 @@
 // Warp roles (10 warps): 0-7 gather (row quarter = warp & 3; the two halves take alternate items) and
 // epilogue (TMEM lane quarter = warp & 3, the halves split the columns); 8 MMA issuer (one elected
 // lane) + TMEM allocation; 9 weight stream (cp.async.bulk ring).
+//   * TMA ROW GATHER (kTma, BEVB200_V6_TMA=1, c_in >= 32; measured and NOT the default).  Warp 10 stages
+//     the operand tiles with cp.async.bulk.tensor ... tile::gather4: one instruction copies the 128-byte
+//     K block of FOUR rows (indices straight from the neighbour table, -1 / out-of-range rows arrive as
+//     zeros) into the SWIZZLE_128B tile and completes on the stage's mbarrier by byte count; warps 0-7
+//     only run epilogues.  The copies bypass the LSU data pipe, but the TMA unit's gather4 rate is the
+//     new bound and it is lower: see the note at the launch.
+#include <cuda.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -34,7 +41,8 @@
 
 namespace bevb200 {
 
-constexpr int kV6Threads = 10 * 32;
+constexpr int kV6Threads = 10 * 32;      // LDGSTS gather (c_in = 16)
+constexpr int kV6ThreadsTma = 11 * 32;   // + the TMA gather warp
 constexpr int kV6TileM = 128;
 constexpr int kV6AStageBytes = kV6TileM * 128;   // 128 rows x 128 B
 constexpr int kV6MaxA = 12, kV6MaxB = 4;
@@ -145,7 +153,18 @@ __device__ __forceinline__ void v6_store_chunk(const V6Params &p, float (&acc)[N
   }
 }
 
-__global__ void __launch_bounds__(kV6Threads, 2) spconv_v6_kernel(const V6Params p) {
+// 4 rows x 128 B of the split image -> 512 contiguous bytes of a SWIZZLE_128B tile (tools/gather4_probe.cu)
+__device__ __forceinline__ void tma_gather4(uint32_t dst_smem, const CUtensorMap *map, int col, int r0, int r1,
+                                            int r2, int r3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+      ::"r"(dst_smem), "l"(map), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar) : "memory");
+}
+
+template <bool kTma>
+__global__ void __launch_bounds__(kTma ? kV6ThreadsTma : kV6Threads, 2)
+spconv_v6_kernel(const V6Params p, const __grid_constant__ CUtensorMap amap) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   __shared__ uint64_t bars[2 * kV6MaxA + 2 * kV6MaxB + 2];
@@ -162,7 +181,7 @@ __global__ void __launch_bounds__(kV6Threads, 2) spconv_v6_kernel(const V6Params
 
   if (tid == 0) {
     for (int s = 0; s < nsa; ++s) {
-      mbar_init(a_full + 8 * s, 4);     // one arrival per gather warp that fills the stage
+      mbar_init(a_full + 8 * s, kTma ? 1 : 4);   // the producer's expect_tx / one arrival per gather warp of the stage
       mbar_init(a_empty + 8 * s, 1);
     }
     for (int s = 0; s < nsb; ++s) {
@@ -218,6 +237,7 @@ __global__ void __launch_bounds__(kV6Threads, 2) spconv_v6_kernel(const V6Params
       int rs = p.r_shift;
       while ((1 << rs) > t_end - tb) --rs;
       const int r_cur = 1 << rs, n_items = nkb << rs;
+      if constexpr (!kTma) {
       int s = gs + par;     // ... of this warp's first item of the group (nsa >= 2)
       uint32_t ph = gph;
       if (s >= nsa) { s -= nsa; ph ^= 1u; }
@@ -318,6 +338,7 @@ __global__ void __launch_bounds__(kV6Threads, 2) spconv_v6_kernel(const V6Params
         }
         pend0 = pend = -1;
       }
+      }  // !kTma
       // ------------------------------- epilogue of the group --------------------------------
       mbar_wait(acc_full, acc_ph);
       acc_ph ^= 1u;
@@ -415,7 +436,7 @@ __global__ void __launch_bounds__(kV6Threads, 2) spconv_v6_kernel(const V6Params
       }
       tb += r_cur;
     }
-  } else {
+  } else if (warp == 9) {
     // =============================== weight stream =======================================
     if (lane == 0) {
       const int n_bstages = p.merged ? (nkb + 1) / 2 : nkb;
@@ -437,6 +458,58 @@ __global__ void __launch_bounds__(kV6Threads, 2) spconv_v6_kernel(const V6Params
       }
     }
     __syncwarp();
+  } else if constexpr (kTma) {
+    // =============================== TMA row gather (warp 10) ============================
+    // Lane l owns rows 4 l .. 4 l + 3 of every tile: one gather4 per lane and item, 512 bytes each.
+    const int cin_shift = p.cin_shift, cin_mask = p.c_in - 1, kvol = p.kvol;
+    const long long nbr_stride = p.nbr_stride;
+    const bool vec = (nbr_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(p.nbr) & 15) == 0;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tb = t_begin; tb < t_end;) {
+      int rs = p.r_shift;
+      while ((1 << rs) > t_end - tb) --rs;
+      const int r_cur = 1 << rs, n_items = nkb << rs;
+      auto load_idx = [&](int i) {
+        const int kb = i >> rs, r = i & (r_cur - 1);
+        const int row = (tb + r) * kV6TileM + 4 * lane;
+        const int k0 = (kb * 32) >> cin_shift;
+        int4 v = make_int4(-1, -1, -1, -1);
+        if (k0 < kvol) {
+          const int32_t *src = p.nbr + (long long)k0 * nbr_stride + row;
+          if (vec && row + 3 < n_out) {
+            v = __ldg(reinterpret_cast<const int4 *>(src));
+          } else {
+            if (row < n_out) v.x = __ldg(src);
+            if (row + 1 < n_out) v.y = __ldg(src + 1);
+            if (row + 2 < n_out) v.z = __ldg(src + 2);
+            if (row + 3 < n_out) v.w = __ldg(src + 3);
+          }
+        }
+        return v;
+      };
+      constexpr int PF = 4;      // items whose indices are in flight ahead of the copies
+      int4 vq[PF];
+#pragma unroll
+      for (int j = 0; j < PF; ++j) vq[j] = j < n_items ? load_idx(j) : make_int4(-1, -1, -1, -1);
+      for (int ibase = 0; ibase < n_items; ibase += PF) {
+#pragma unroll
+        for (int j = 0; j < PF; ++j) {
+          const int i = ibase + j;
+          if (i >= n_items) break;
+          const int4 v = vq[j];
+          if (i + PF < n_items) vq[j] = load_idx(i + PF);
+          const int col = (((i >> rs) * 32) & cin_mask) * 2;     // bf16 elements into the row image
+          mbar_wait(a_empty + 8 * s, ph ^ 1u);
+          if (lane == 0) mbar_arrive_expect_tx(a_full + 8 * s, (uint32_t)kV6AStageBytes);
+          __syncwarp();
+          tma_gather4(a_ring + (uint32_t)s * (uint32_t)kV6AStageBytes + (uint32_t)lane * 512u, &amap, col, v.x, v.y,
+                      v.z, v.w, a_full + 8 * s);
+          if (++s == nsa) { s = 0; ph ^= 1u; }
+        }
+      }
+      tb += r_cur;
+    }
   }
   (void)r_max;
   tc_fence_before();
@@ -567,6 +640,34 @@ int spconv_v6_split_rows(const float *features, int n_cap, const int32_t *n_dev,
   return BEVB200_OK;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library does not link libcuda)
+typedef CUresult (*V6EncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static V6EncodeTiled v6_encode_fn() {
+  static V6EncodeTiled fn = [] {
+    void *f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return (V6EncodeTiled)f;
+  }();
+  return fn;
+}
+// the split image as a 2-D bf16 tensor [rows][c_in * 2], one 128-byte K block of one row per box
+static bool v6_row_map(const void *split, int rows, int c_in, CUtensorMap *map) {
+  V6EncodeTiled enc = v6_encode_fn();
+  if (!enc) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)c_in * 2, (cuuint64_t)(rows > 0 ? rows : 1)};
+  const cuuint64_t strides[1] = {(cuuint64_t)c_in * 4};
+  const cuuint32_t box[2] = {64, 1};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(split), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static int env_int(const char *name, int dflt) {
   const char *e = getenv(name);
   return e ? atoi(e) : dflt;
@@ -631,8 +732,21 @@ int spconv_v6_forward(const void *features_split, const void *packed, const int3
   const int n_tiles = (n_out + kV6TileM - 1) / kV6TileM;
   int grid = ctas * kNumSMs;
   if (grid > n_tiles) grid = n_tiles;
-  BEVB200_CUDA(cudaFuncSetAttribute(spconv_v6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  BEVB200_LAUNCH(spconv_v6_kernel, grid, kV6Threads, smem, st, p);
+  // operand gather: LDGSTS.  BEVB200_V6_TMA=1 selects the TMA gather4 producer for c_in >= 32 -- bit-identical
+  // results, but measured 2x SLOWER (5.10 vs 2.74 ms for the 21 convs): one warp issues a gather4 every ~90-190 clk
+  // and the unit tops out at ~23 B/clk/SM on valid rows, ~13 B/clk/SM with 55 % out-of-range rows, against the
+  // ~26 B/clk/SM the LDGSTS kernel sustains end to end (tools/gather4_probe.cu, profiles/r2_gather4_probe.txt).
+  static const int tma_env = env_int("BEVB200_V6_TMA", 0);
+  CUtensorMap amap;
+  memset(&amap, 0, sizeof(amap));
+  if (tma_env != 0 && c_in >= 32) {
+    BEVB200_REQUIRE(v6_row_map(features_split, n_in, c_in, &amap), "cuTensorMapEncodeTiled failed for the row image");
+    BEVB200_CUDA(cudaFuncSetAttribute(spconv_v6_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BEVB200_LAUNCH(spconv_v6_kernel<true>, grid, kV6ThreadsTma, smem, st, p, amap);
+  } else {
+    BEVB200_CUDA(cudaFuncSetAttribute(spconv_v6_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BEVB200_LAUNCH(spconv_v6_kernel<false>, grid, kV6Threads, smem, st, p, amap);
+  }
   return BEVB200_OK;
 }
 
