@@ -72,7 +72,7 @@ _SIGNATURES = {
     "bevb200_spconv_forward_split": (c_int, [_P, _P, _P, ctypes.c_longlong, c_int, c_int, _P] + [c_int] * 3
                                      + [_P, _P, _P, c_int, _P, _P, _P]),
     "bevb200_rulebook_transpose": (c_int, [_P, c_int, c_int, c_int, _P, _P]),
-    "bevb200_spconv_backward_workspace_bytes": (c_size_t, [c_int] * 4),
+    "bevb200_spconv_backward_workspace_bytes": (c_size_t, [c_int] * 5),
     "bevb200_spconv_backward": (c_int, [_P] * 5 + [c_int] * 6 + [_P, _P, _P, c_size_t, _P]),
     "bevb200_sparse_to_dense": (c_int, [_P, _P, c_int, c_int, c_int, _P, c_int, ctypes.c_longlong, _P, _P]),
     "bevb200_encoder_create": (c_int, [c_int, _P, _P, c_int, _P]),

@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libbevfusion_b200.so")
-SOURCES = ["common.cu", "bevpool.cu", "bevpool_lift.cu", "voxelize.cu", "scatter.cu", "depthmap.cu", "rulebook.cu", "spconv_simt.cu", "spconv_tc.cu", "spconv_v6.cu", "encoder.cu", "spconv_bwd.cu"]
+SOURCES = ["common.cu", "bevpool.cu", "bevpool_lift.cu", "voxelize.cu", "scatter.cu", "depthmap.cu", "rulebook.cu", "spconv_simt.cu", "spconv_tc.cu", "spconv_v6.cu", "encoder.cu", "spconv_bwd.cu", "spconv_wgrad_tc.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",

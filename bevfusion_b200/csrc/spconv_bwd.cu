@@ -19,6 +19,10 @@ int spconv_forward_simt(const float *features, const float *weight, const int32_
                         int n_out, int c_in, int c_out, int kvol, const float *scale,
                         const float *shift, const float *residual, int relu, float *out,
                         cudaStream_t st);
+bool spconv_wgrad_tc_ok(int c_in, int c_out, int kvol);
+size_t spconv_wgrad_tc_workspace_bytes(int n_in, int n_out, int c_in, int c_out, int kvol);
+int spconv_wgrad_tc(const float *features, const float *out_grad, const int32_t *nbr, int n_in, int n_out,
+                    int c_in, int c_out, int kvol, float *weight_grad, void *workspace, cudaStream_t st);
 int spconv_forward_tc(const float *features, const float *weight, const float *packed,
                       const int32_t *nbr, int n_in, int n_out, int c_in, int c_out, int kvol,
                       const float *scale, const float *shift, const float *residual, int relu,
@@ -201,11 +205,13 @@ int bevb200_rulebook_transpose(const int32_t *nbr, int kernel_volume, int n_out,
   return BEVB200_OK;
 }
 
-size_t bevb200_spconv_backward_workspace_bytes(int n_out, int c_in, int c_out, int kernel_volume) {
-  if (n_out < 0 || c_in <= 0 || c_out <= 0 || kernel_volume <= 0) return 0;
+size_t bevb200_spconv_backward_workspace_bytes(int n_in, int n_out, int c_in, int c_out, int kernel_volume) {
+  if (n_in < 0 || n_out < 0 || c_in <= 0 || c_out <= 0 || kernel_volume <= 0) return 0;
   const size_t w = align_up((size_t)kernel_volume * c_in * c_out * sizeof(float));
   const size_t chunks = ((size_t)n_out + kWgChunk - 1) / kWgChunk;
-  return w * (1 + (chunks ? chunks : 1));     // transposed weights + one partial dW per chunk of output rows
+  const size_t simt = w * (chunks ? chunks : 1);          // one partial dW per chunk of output rows
+  const size_t tc = spconv_wgrad_tc_workspace_bytes(n_in, n_out, c_in, c_out, kernel_volume);   // split images + partials
+  return w + (simt > tc ? simt : tc);                     // transposed weights + the larger of the two
 }
 
 int bevb200_spconv_backward(const float *features, const float *weight, const float *out_grad,
@@ -225,7 +231,8 @@ int bevb200_spconv_backward(const float *features, const float *weight, const fl
     return BEVB200_OK;
   }
   BEVB200_REQUIRE(features && out_grad && nbr && nbr_t, "null argument");
-  if (workspace == nullptr || workspace_bytes < bevb200_spconv_backward_workspace_bytes(n_out, c_in, c_out, kernel_volume)) {
+  if (workspace == nullptr ||
+      workspace_bytes < bevb200_spconv_backward_workspace_bytes(n_in, n_out, c_in, c_out, kernel_volume)) {
     snprintf(g_last_error, sizeof(g_last_error), "spconv_backward: workspace too small");
     return BEVB200_EWORKSPACE;
   }
@@ -241,7 +248,12 @@ int bevb200_spconv_backward(const float *features, const float *weight, const fl
     rc = spconv_forward_tc(out_grad, wt, nullptr, nbr_t, n_out, n_in, c_out, c_in, kernel_volume, nullptr,
                            nullptr, nullptr, 0, precision, input_grad, st);
   if (rc) return rc;
-  // dW: per-chunk partials, then an ordered reduction (no atomics)
+  // dW on the tensor cores (spconv_wgrad_tc.cu) for the tensor-core precisions and channel counts 32 / 64 / 128 ...
+  if ((precision == BEVB200_PREC_BF16X3 || precision == BEVB200_PREC_TF32) && spconv_wgrad_tc_ok(c_in, c_out, kernel_volume) &&
+      (uintptr_t)features % 16 == 0 && (uintptr_t)out_grad % 16 == 0)
+    return spconv_wgrad_tc(features, out_grad, nbr, n_in, n_out, c_in, c_out, kernel_volume, weight_grad,
+                           (char *)workspace + align_up(wbytes), st);
+  // ... else SIMT: per-chunk partials, then an ordered reduction (no atomics)
   const int n_chunks = (n_out + kWgChunk - 1) / kWgChunk;
   float *partial = (float *)((char *)workspace + align_up(wbytes));
   dim3 grid(n_chunks, kernel_volume);

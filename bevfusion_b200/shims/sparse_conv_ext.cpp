@@ -115,7 +115,7 @@ std::vector<torch::Tensor> indice_conv_backward(torch::Tensor features, torch::T
               bevb200_last_error());
   auto din = torch::empty({n_in, cin}, f.options());
   auto dw = torch::empty_like(w);
-  auto ws = torch::empty({(int64_t)bevb200_spconv_backward_workspace_bytes(n_out, cin, cout, K) + 256}, f.options().dtype(torch::kUInt8));
+  auto ws = torch::empty({(int64_t)bevb200_spconv_backward_workspace_bytes(n_in, n_out, cin, cout, K) + 256}, f.options().dtype(torch::kUInt8));
   TORCH_CHECK(0 == bevb200_spconv_backward(f.data_ptr<float>(), w.data_ptr<float>(), g.data_ptr<float>(), nbr.data_ptr<int>(),
                                            nbr_t.data_ptr<int>(), n_in, n_out, cin, cout, K, BEVB200_PREC_BF16X3,
                                            din.data_ptr<float>(), dw.data_ptr<float>(), ws.data_ptr(), (size_t)ws.numel(),

@@ -310,7 +310,7 @@ def sparse_conv_backward(features, weight, out_grad, nbr, nbr_t=None, precision=
     with torch.cuda.device(dev):
         din = torch.empty((n_in, c_in), dtype=torch.float32, device=dev)
         dw = torch.empty_like(weight)
-        ws = torch.empty(max(L.bevb200_spconv_backward_workspace_bytes(int(n_out), c_in, c_out, kvol), 256),
+        ws = torch.empty(max(L.bevb200_spconv_backward_workspace_bytes(int(n_in), int(n_out), c_in, c_out, kvol), 256),
                          dtype=torch.uint8, device=dev)
         rc = L.bevb200_spconv_backward(_C.ptr(features), _C.ptr(weight), _C.ptr(out_grad), _C.ptr(nbr),
                                        _C.ptr(nbr_t), n_in, n_out, c_in, c_out, kvol, int(precision),

@@ -447,12 +447,14 @@ BEVB200_API int bevb200_spconv_forward_split(const void *features_split, const v
  * nbr_t [K, n_in] is the transposed neighbour table from bevb200_rulebook_transpose()
  * (nbr_t[k, j] = the output row that input row j feeds through offset k, or -1).
  * The input gradient runs the forward implicit-GEMM kernel on (out_grad, W^T, nbr_t) in the
- * requested precision; the weight gradient sums fixed 2048-row chunks into per-chunk partials and
- * adds those in ascending chunk order: no atomics, bit-reproducible run to run.
- * workspace: bevb200_spconv_backward_workspace_bytes() (the transposed weights + the partials). */
+ * requested precision.  The weight gradient sums chunks of rows into per-chunk partials and adds those in
+ * ascending chunk order: no atomics, bit-reproducible run to run -- on the tensor cores for BEVB200_PREC_BF16X3 /
+ * _TF32 and c_in, c_out in {32, 64, 128} (spconv_wgrad_tc.cu: MN-major tcgen05 MMAs over the bf16 hi/lo
+ * images of the gathered feature rows and the out-grad rows; BEVB200_WGRAD_TC=0 keeps the SIMT kernel), else SIMT.
+ * workspace: bevb200_spconv_backward_workspace_bytes() (the transposed weights, the operand images, the partials). */
 BEVB200_API int bevb200_rulebook_transpose(const int32_t *nbr, int kernel_volume, int n_out, int n_in,
                                int32_t *nbr_t, void *stream);
-BEVB200_API size_t bevb200_spconv_backward_workspace_bytes(int n_out, int c_in, int c_out, int kernel_volume);
+BEVB200_API size_t bevb200_spconv_backward_workspace_bytes(int n_in, int n_out, int c_in, int c_out, int kernel_volume);
 BEVB200_API int bevb200_spconv_backward(const float *features, const float *weight, const float *out_grad,
                             const int32_t *nbr, const int32_t *nbr_t, int n_in, int n_out, int c_in,
                             int c_out, int kernel_volume, int precision, float *input_grad,

@@ -257,14 +257,15 @@ def test_weight_gradient_is_reproducible(cuda):
     feat = torch.randn(n, cin, device=cuda, generator=g)
     W = torch.randn(27, cin, cout, device=cuda, generator=g) / 30
     gout = torch.randn(n, cout, device=cuda, generator=g)
-    runs = [ops.sparse_conv_backward(feat, W, gout, rb.nbr, precision=0) for _ in range(3)]
-    for din, dw in runs[1:]:
-        assert bool(torch.equal(dw, runs[0][1])) and bool(torch.equal(din, runs[0][0]))
-    # and it is the right gradient: dW[k] = sum_o f[nbr[k, o]]^T g[o]
-    k = 5
-    valid = rb.nbr[k] >= 0
-    want = feat[rb.nbr[k][valid].long()].double().t() @ gout[valid].double()
-    assert float((runs[0][1][k].double() - want).abs().max()) <= 1e-4 * float(want.abs().max())
+    for prec in [0] + ([3] if tc_available(cuda) else []):       # SIMT kernel / tensor-core kernel (spconv_wgrad_tc.cu)
+        runs = [ops.sparse_conv_backward(feat, W, gout, rb.nbr, precision=prec) for _ in range(3)]
+        for din, dw in runs[1:]:
+            assert bool(torch.equal(dw, runs[0][1])) and bool(torch.equal(din, runs[0][0]))
+        # and it is the right gradient: dW[k] = sum_o f[nbr[k, o]]^T g[o]   (every offset, many row chunks)
+        for k in range(27):
+            valid = rb.nbr[k] >= 0
+            want = feat[rb.nbr[k][valid].long()].double().t() @ gout[valid].double()
+            assert float((runs[0][1][k].double() - want).abs().max()) <= 1e-4 * float(want.abs().max()), (prec, k)
 
 
 def test_native_plan_vs_python_loop(cuda):
@@ -426,7 +427,7 @@ def test_lidar_branch_full_size(cuda):
 
 
 @pytest.mark.parametrize("geom", list(GEOMS))
-@pytest.mark.parametrize("cin,cout", [(5, 16), (16, 32), (64, 64), (128, 128)])
+@pytest.mark.parametrize("cin,cout", [(5, 16), (16, 32), (32, 32), (32, 64), (64, 64), (64, 128), (128, 128)])
 def test_backward_vs_oracle(cuda, geom, cin, cout):
     """indice_conv_backward: input and weight gradients vs the float64 oracle (<= 1e-4 rel)."""
     from bevfusion_b200.spconv import ops
