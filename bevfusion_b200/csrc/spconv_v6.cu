@@ -668,6 +668,16 @@ static bool v6_row_map(const void *split, int rows, int c_in, CUtensorMap *map) 
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// split image with an explicit padded channel count (multiple of 16, >= c_in): the filter-gradient kernel wants
+// whole 128-byte slabs (spconv_wgrad_tc.cu)
+int spconv_v6_split_rows_padded(const float *features, int n, int c_in, int c_eff, void *split, cudaStream_t st) {
+  BEVB200_REQUIRE(c_eff >= c_in && c_eff % 16 == 0 && c_in >= 1, "bad padded channel count");
+  if (n <= 0) return BEVB200_OK;
+  BEVB200_LAUNCH(spconv_v6_split_rows_kernel, grid_for((long long)n * (c_eff / 8), 256), 256, 0, st, features, n,
+                 (const int32_t *)nullptr, c_in, c_eff, (uint8_t *)split);
+  return BEVB200_OK;
+}
+
 static int env_int(const char *name, int dflt) {
   const char *e = getenv(name);
   return e ? atoi(e) : dflt;
