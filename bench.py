@@ -889,8 +889,9 @@ def run_ours(args, rank, world, local_rank):
                      "spconv_fwd_ms_21_convs": round(conv_ms, 4), "spconv_bwd_ms_21_convs": round(conv_bwd_ms, 4),
                      "note": "BASELINE config #2 asks for fwd+bwd: bev_pool backward = write stream through perm; spconv "
                              "backward per conv = input gradient (forward kernel on the transposed neighbour table, "
-                             "bf16x3) + filter gradient (SIMT outer products, per-chunk partials + ordered reduction: "
-                             "bit-reproducible); each launch timed alone"},
+                             "bf16x3) + filter gradient (tensor cores: MN-major tcgen05 MMAs over the bf16 hi / lo "
+                             "images, per-chunk partials + ordered reduction: bit-reproducible; spconv_wgrad_tc.cu); "
+                             "each backward call timed alone"},
         "next_rows": next_rows,
         "roofline": dominant, "roofline_bev_pool": roof_pool, "roofline_bev_pool_op": roof_pool_op,
         "roofline_encoder": roof_enc, "roofline_voxelize": roof_vox,

@@ -561,6 +561,48 @@ print("variant-4 ok")
     assert r.returncode == 0 and "variant-4 ok" in r.stdout, r.stdout + r.stderr
 
 
+def test_gather_variants_are_bit_identical(cuda):
+    """The operand gather of the generation-6 kernel has two selectable forms -- LDGSTS (default) and the TMA gather4
+    producer warp (BEVB200_V6_TMA=1) -- and generation 5 gathers fp32 rows and splits them on the fly
+    (BEVB200_SPCONV_TC_VARIANT=5).  They only differ in HOW the same bf16 hi / lo tile reaches the tensor core: results
+    must be bit-identical.  The switches are read once per process, so each form runs in a child process and prints a
+    checksum; many tiles, low / high neighbour density, SubM and strided rulebooks."""
+    import subprocess
+    import sys
+    if not tc_available(cuda):
+        pytest.skip("no tcgen05 path")
+    code = r"""
+import hashlib, numpy as np, torch
+from bevfusion_b200.spconv import ops
+dev = torch.device("cuda:0")
+h = hashlib.sha256()
+for dens, shape in ((0.03, [96, 90, 21]), (0.5, [40, 36, 11])):
+    rng = np.random.default_rng(5)
+    vol = shape[0] * shape[1] * shape[2]
+    flat = np.sort(rng.choice(vol, size=int(vol * dens), replace=False))
+    idx = np.stack([np.zeros_like(flat), flat // (shape[1] * shape[2]), (flat // shape[2]) % shape[1], flat % shape[2]],
+                   1).astype(np.int32)
+    for subm, st in ((True, 1), (False, 2)):
+        rb, _ = ops.get_rulebook(torch.from_numpy(idx).to(dev), 1, shape, 3, st, 1, 1, 0, subm)
+        for cin, cout in ((16, 16), (16, 32), (32, 32), (64, 64), (64, 128), (128, 128)):
+            g = torch.Generator(device=dev).manual_seed(cin + cout)
+            f = torch.randn(idx.shape[0], cin, device=dev, generator=g)
+            w = torch.randn(27, cin, cout, device=dev, generator=g) / (3 * cin)
+            for rep in range(2):
+                out = ops.sparse_conv(f, w, rb.nbr, rb.n_out, precision=3)
+                h.update(out.cpu().numpy().tobytes())
+print("checksum", h.hexdigest())
+"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sums = {}
+    for name, extra in (("default", {}), ("tma gather4", {"BEVB200_V6_TMA": "1"}), ("generation 5", {"BEVB200_SPCONV_TC_VARIANT": "5"})):
+        env = dict(os.environ, PYTHONPATH=os.pathsep.join([root] + os.environ.get("PYTHONPATH", "").split(os.pathsep)), **extra)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "checksum" in r.stdout, name + ": " + r.stdout + r.stderr
+        sums[name] = r.stdout.split("checksum")[1].split()[0]
+    assert len(set(sums.values())) == 1, sums
+
+
 def test_fused_indice_conv_and_half_backward_shims(cuda):
     """the remaining sparse_conv_ext entry points a 3-D model can reach: fused_indice_conv_* (bias in the
     epilogue; fused_spconv_ops.h:28-131) and indice_conv_backward_half (spconv_ops.h:363-456 on halves)."""
