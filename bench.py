@@ -669,11 +669,19 @@ def run_ours(args, rank, world, local_rank):
     out_stream = torch.cuda.Stream(device=device)
 
     def e2e_pipeline(host_tensors, compute, nframes):
-        """three streams: H2D of frame i+1 (copy stream), compute of frame i (main), D2H of frame i-1 (out stream)"""
+        """three streams: H2D of frame i+1 (copy stream), compute of frame i (main), D2H of frame i-1 (out stream).
+        The compute of each of the two input buffer sets is captured once as a CUDA graph (the API is sync-free, so a
+        user can do exactly that) and replayed per frame; every frame still copies its inputs in and its results out."""
         bufs = [[torch.empty(h.shape, dtype=h.dtype, device=device) for h in host_tensors] for _ in range(2)]
         ready = [torch.cuda.Event() for _ in range(2)]
         freed = [torch.cuda.Event() for _ in range(2)]
+        out_done = [torch.cuda.Event() for _ in range(2)]
         done = torch.cuda.Event()
+        for bset in bufs:                                   # defined inputs for the capture's warm-up runs
+            for dst, src in zip(bset, host_tensors):
+                dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        graphs = [hp.capture(compute, *bset) for bset in bufs]
 
         def stage_in(i):
             with torch.cuda.stream(copy_stream):
@@ -685,20 +693,23 @@ def run_ours(args, rank, world, local_rank):
         def run(n):
             for f in freed:
                 f.record(main_stream)
+            for f in out_done:
+                f.record(out_stream)
             stage_in(0)
             for i in range(n):
                 if i + 1 < n:
                     stage_in(i + 1)
                 main_stream.wait_event(ready[i % 2])
-                bev, lidar = compute(*bufs[i % 2])
+                main_stream.wait_event(out_done[i % 2])   # this graph's output buffers have been read out
+                g, (bev, lidar) = graphs[i % 2]
+                g.replay()
                 freed[i % 2].record(main_stream)
                 done.record(main_stream)
                 with torch.cuda.stream(out_stream):       # D2H of the step's results
                     out_stream.wait_event(done)
                     bev_h.copy_(bev, non_blocking=True)
                     lid_h.copy_(lidar, non_blocking=True)
-                    bev.record_stream(out_stream)
-                    lidar.record_stream(out_stream)
+                    out_done[i % 2].record(out_stream)
             main_stream.wait_stream(out_stream)
 
         run(2)
@@ -707,7 +718,9 @@ def run_ours(args, rank, world, local_rank):
         run(nframes)
         e1.record()
         barrier()
-        return max_over_ranks(e0.elapsed_time(e1)) / nframes
+        ms = max_over_ranks(e0.elapsed_time(e1)) / nframes
+        del graphs
+        return ms
 
     dh, ch = hp.lift_inputs(seed=rank)
     ph = hp.points_host
@@ -871,7 +884,10 @@ def run_ours(args, rank, world, local_rank):
         "e2e": {"value": round(world * 1000.0 / e2e_ms, 3), "unit": "frames/s", "ms_per_step": round(e2e_ms, 3),
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "inputs": "pinned host: softmax depth [1,6,118,32,88] + context [1,6,32,88,80] (what the camera branch "
-                          "hands the view transform, depth_lss.py:92-97) + points; outputs: both BEV maps to pinned host"},
+                          "hands the view transform, depth_lss.py:92-97) + points; outputs: both BEV maps to pinned host",
+                "compute": "BEVPoolPlan.lift + voxelize + SparseEncoder captured once per input buffer set as a CUDA graph "
+                           "(the API is sync-free) and replayed; H2D of frame i+1 / compute of frame i / D2H of frame i-1 on "
+                           "three streams, every frame copies its inputs in and its results out"},
         "e2e_materialised": {"value": round(world * 1000.0 / e2e_mat_ms, 3), "unit": "frames/s",
                              "ms_per_step": round(e2e_mat_ms, 3), "h2d_bytes_per_step": h2d_mat,
                              "d2h_bytes_per_step": d2h, "steps": mat_steps,
