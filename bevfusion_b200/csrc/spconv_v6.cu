@@ -202,6 +202,12 @@ spconv_v6_kernel(const V6Params p, const __grid_constant__ CUtensorMap amap) {
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
+  // Programmatic dependent launch: everything above (barriers, TMEM) ran while the previous kernel of the stream was
+  // still draining; its results (feature image, row count) are only touched below.  Without the launch attribute both
+  // instructions are no-ops.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
   // this CTA's contiguous range of 128-row tiles (balanced to +-1 tile over the grid)
   int n_out = p.n_out;
   if (p.n_out_dev) n_out = min(n_out, __ldg(p.n_out_dev));
@@ -755,7 +761,26 @@ int spconv_v6_forward(const void *features_split, const void *packed, const int3
     BEVB200_LAUNCH(spconv_v6_kernel<true>, grid, kV6ThreadsTma, smem, st, p, amap);
   } else {
     BEVB200_CUDA(cudaFuncSetAttribute(spconv_v6_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    BEVB200_LAUNCH(spconv_v6_kernel<false>, grid, kV6Threads, smem, st, p, amap);
+    // BEVB200_V6_PDL=1 (default): programmatic stream serialisation -- the kernel's prologue overlaps the tail of
+    // the previous kernel in the stream (21 back-to-back convs per frame)
+    static const int pdl_env = env_int("BEVB200_V6_PDL", 1);
+    if (pdl_env) {
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3((unsigned)grid);
+      cfg.blockDim = dim3((unsigned)kV6Threads);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      BEVB200_CUDA(cudaLaunchKernelEx(&cfg, spconv_v6_kernel<false>, p, amap));
+      ++g_launch_count;
+    } else {
+      BEVB200_LAUNCH(spconv_v6_kernel<false>, grid, kV6Threads, smem, st, p, amap);
+    }
   }
   return BEVB200_OK;
 }
