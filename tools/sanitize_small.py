@@ -33,7 +33,14 @@ for (cin, cout) in ((16, 32), (64, 64), (5, 16)):
             o = ops.sparse_conv(f, w, rb.nbr, rb.n_out, precision=prec)
         o = ops.sparse_conv(f, w, rb.nbr, rb.n_out, precision=3, packed=ops.pack_weights(w, 3))
         ops.sparse_conv_backward(f, w, torch.randn_like(o), rb.nbr, precision=1)
+        ops.sparse_conv_backward(f, w, torch.randn_like(o), rb.nbr, precision=3)     # tensor-core filter gradient
         rb.pairs()
+# tensor-core filter gradient at the remaining slab counts (32 / 128 channels on either side)
+for (cin, cout) in ((32, 32), (32, 64), (128, 128), (64, 128)):
+    f = torch.randn(n, cin, device=dev)
+    rb, _ = ops.get_rulebook(ti, Bn, shape, 3, 1, 1, 1, 0, True)
+    w = torch.randn(27, cin, cout, device=dev)
+    ops.sparse_conv_backward(f, w, torch.randn(rb.n_out, cout, device=dev), rb.nbr, precision=3)
 # fused voxelize + mean, DynamicScatter fwd / bwd (all reductions), LiDAR depth images, in-place layouts
 from bevfusion_b200 import synthetic as S
 from bevfusion_b200.scatter_points import dynamic_scatter
