@@ -1,0 +1,8 @@
+timeout 2400 python -m pytest tests -m gpu -q > gpurun_out/tests_final2.log 2>&1; tail -4 gpurun_out/tests_final2.log
+timeout 600 python -c "import __graft_entry__ as g; g.smoke(); print('SMOKE OK')" 2>&1 | tail -1
+timeout 1500 python bench.py > gpurun_out/bench_final2.json 2> gpurun_out/bench_final2.err; tail -3 gpurun_out/bench_final2.err
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/bench_final2.json').read().strip().splitlines()[-1])
+print('value', d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], 'stages', d['stages_ms'], 'roofline', d['roofline']['frac'], d['roofline']['ms'], 'training', d['training']['spconv_bwd_ms_21_convs'])
+PY
