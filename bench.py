@@ -474,7 +474,6 @@ def c4_leg(hp, device, steps, warmup, world):
         pts = hp.points_host.to(device)
         fuser_in = torch.zeros(1, 80 + 256, 180, 180, device=device)
         cam_stream, lid_stream = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
-        main = torch.cuda.current_stream(device)
         marks = {}
 
         def frame(timed=False):
@@ -483,6 +482,7 @@ def c4_leg(hp, device, steps, warmup, world):
                     e = torch.cuda.Event(enable_timing=True)
                     e.record(stream)
                     marks.setdefault(name, []).append(e)
+            main = torch.cuda.current_stream(device)      # the capturing stream when the frame is recorded as a graph
             with torch.no_grad():
                 mark("t0", main)
                 cam_stream.wait_stream(main); lid_stream.wait_stream(main)
@@ -529,6 +529,40 @@ def c4_leg(hp, device, steps, warmup, world):
                "glue": "plain torch fp32 tensors, TF32 allowed for cuDNN / cuBLAS, random frozen weights, eval-mode BN; "
                        "37 M parameters; eager launches (not graph-captured)",
                "target": ">= 25 frames/s on 1 GPU (BASELINE.json north_star)"}
+        # the same frame recorded once as a CUDA graph (static image / point buffers) and replayed: what a deployment
+        # does, and possible because nothing in the hot path synchronises with the host
+        try:
+            side = torch.cuda.Stream(device=device)
+            side.wait_stream(torch.cuda.current_stream(device))
+            with torch.cuda.stream(side):
+                frame()
+            torch.cuda.current_stream(device).wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                gout = frame()
+            for _ in range(3):
+                g.replay()
+            torch.cuda.synchronize()
+            if world > 1:
+                torch.distributed.barrier()
+            e0.record()
+            for _ in range(steps):
+                g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+            if world > 1:
+                torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            gms = float(t.item()) / steps
+            same = bool(torch.equal(gout[0], out[0]))
+            res["graph"] = {"frames_per_s": round(world * 1000.0 / gms, 2), "ms_per_frame": round(gms, 3),
+                            "boxes_equal_to_eager": same}
+            del g, gout
+        except Exception as exc:                       # a glue op that cannot be captured: report, keep the eager line
+            res["graph"] = {"unavailable": "%s: %s" % (type(exc).__name__, str(exc)[:200])}
+            if world > 1:                              # keep the ranks' collectives aligned
+                pass
         del glue
         return res
     finally:
