@@ -18,6 +18,8 @@
 // single-pass decoupled-look-back scan.  Strided convs are built output-side: the outputs of level l+1
 // look their <= K inputs up in level l's bitmap (no scatter, no -1 fill pass, coalesced writes); one
 // thread walks the kz column of one (kx, ky) so consecutive lookups hit the same word.
+#include <stdlib.h>
+
 #include <algorithm>
 #include <new>
 #include <vector>
@@ -32,6 +34,10 @@ size_t spconv_v6_packed_bytes(int c_in, int c_out, int kvol);
 int spconv_v6_pack_weights(const float *weight, int c_in, int c_out, int kvol, void *packed, cudaStream_t st);
 int spconv_v6_split_rows(const float *features, int n_cap, const int32_t *n_dev, int c_in, void *split,
                          cudaStream_t st);
+int spconv_v6_forward_ex(const void *features_split, const void *packed, const int32_t *nbr, long long nbr_stride,
+                         int n_in, int n_out, const int32_t *n_out_dev, int c_in, int c_out, int kvol,
+                         const float *scale, const float *shift, const float *residual, const void *residual_split,
+                         int relu, float *out, void *out_split, cudaStream_t st);
 int spconv_v6_forward(const void *features_split, const void *packed, const int32_t *nbr, long long nbr_stride,
                       int n_in, int n_out, const int32_t *n_out_dev, int c_in, int c_out, int kvol,
                       const float *scale, const float *shift, const float *residual, int relu, float *out,
@@ -459,8 +465,11 @@ int bevb200_encoder_create(int in_channels, const int32_t *sparse_shape_host, co
     e->convs.push_back(cv);
     c_prev = cv.d.c_out;
   }
+  // A residual is read from the source conv's SPLIT image -- hi + lo is the value to 2^-17 -- so only the last conv,
+  // whose rows dense() scatters, writes fp32 rows; BEVB200_ENCODER_F32_RESIDUAL=1 restores the fp32 residual copies.
+  static const bool f32_residual = [] { const char *v = getenv("BEVB200_ENCODER_F32_RESIDUAL"); return v && atoi(v) != 0; }();
   for (EConv &cv : e->convs)
-    if (cv.d.residual_from >= 0) e->convs[cv.d.residual_from].want_fp32 = true;
+    if (f32_residual && cv.d.residual_from >= 0) e->convs[cv.d.residual_from].want_fp32 = true;
   e->param_bytes = poff;
   *out = e;
   return BEVB200_OK;
@@ -626,6 +635,7 @@ int bevb200_encoder_forward(bevb200_encoder_t *e, const void *params, const floa
   split_turn[0] = 1;
   const uint8_t *cur_split = w.split[0][0];
   std::vector<const float *> f32_of(e->convs.size(), nullptr);
+  std::vector<const uint8_t *> split_of(e->convs.size(), nullptr);
   std::vector<char> rb_waited(nr, 0);
   const float *last_f32 = nullptr;
   for (size_t i = 0; i < e->convs.size(); ++i) {
@@ -647,12 +657,18 @@ int bevb200_encoder_forward(bevb200_encoder_t *e, const void *params, const floa
       f32_turn[lo] ^= 1;
       f32_of[i] = of32;
     }
+    // residual: the source conv's fp32 rows if it wrote them, else its split image (which may be the buffer this conv
+    // writes: the two split buffers of a level alternate and a block's input is two convs back -- safe, see spconv_v6.cu)
     const float *res = cv.d.residual_from >= 0 ? f32_of[cv.d.residual_from] : nullptr;
-    rc = spconv_v6_forward(cur_split, pbase + cv.packed_off, w.nbr[cv.rulebook], (long long)caps[lo], caps[cv.level_in],
-                           caps[lo], w.counts[lo], cv.c_in_eff, cv.d.c_out, cv.kvol,
-                           cv.has_scale ? (const float *)(pbase + cv.scale_off) : nullptr,
-                           cv.has_shift ? (const float *)(pbase + cv.shift_off) : nullptr, res, cv.d.relu, of32, osplit, st);
+    const uint8_t *res_split = (cv.d.residual_from >= 0 && res == nullptr) ? split_of[cv.d.residual_from] : nullptr;
+    BEVB200_REQUIRE(cv.d.residual_from < 0 || res || res_split, "residual source has no rows");
+    rc = spconv_v6_forward_ex(cur_split, pbase + cv.packed_off, w.nbr[cv.rulebook], (long long)caps[lo], caps[cv.level_in],
+                              caps[lo], w.counts[lo], cv.c_in_eff, cv.d.c_out, cv.kvol,
+                              cv.has_scale ? (const float *)(pbase + cv.scale_off) : nullptr,
+                              cv.has_shift ? (const float *)(pbase + cv.shift_off) : nullptr, res, res_split, cv.d.relu,
+                              of32, osplit, st);
     if (rc) return rc;
+    split_of[i] = osplit;
     cur_split = osplit;
     last_f32 = of32;
   }

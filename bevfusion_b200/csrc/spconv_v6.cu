@@ -10,7 +10,7 @@
 //   * PRE-SPLIT FEATURES.  A feature row is stored as the bf16 image the tensor core consumes: per
 //     group of 16 channels 32 B of bf16 "hi" followed by 32 B of bf16 "lo" (hi = rn(x), lo = rn(x - hi);
 //     4 bytes per element, like fp32).  The producing conv writes that image from its epilogue (and
-//     fp32 rows only where a residual or dense() needs them); the split is done once per row instead
+//     fp32 rows only where dense() needs them; a residual is read from a split image too); the split is done once per row instead
 //     of once per (row, kernel offset) visit.
 //   * NO CONVERT WARPS, NO A RING IN TMEM.  Gather warps copy the rows with cp.async.cg straight into
 //     the K-major SWIZZLE_128B tile the UMMA descriptor describes (row r at r*128 B, 16-byte chunk c at
@@ -54,6 +54,8 @@ struct V6Params {
   long long nbr_stride;
   const int32_t *n_out_dev;     // optional device-side row count (<= n_out)
   const float *scale, *shift, *residual;
+  const uint8_t *residual_split; // residual rows as a split image (x = hi + lo, exact to 2^-17 |x|): lets a producer
+                                 // skip its fp32 copy; may alias out_split (a lane reads its chunk before writing it)
   float *out;                   // optional fp32 rows [n_out, c_out]
   uint8_t *out_split;           // optional split image [n_out, c_out * 4 B]
   int n_in, n_out;
@@ -128,6 +130,20 @@ __device__ __forceinline__ void v6_store_chunk(const V6Params &p, float (&acc)[N
     for (int j = 0; j < NC / 4; ++j) {
       const float4 rv = __ldg(res + j);
       y[4 * j] += rv.x; y[4 * j + 1] += rv.y; y[4 * j + 2] += rv.z; y[4 * j + 3] += rv.w;
+    }
+  } else if (p.residual_split) {
+    // plain loads (the image may be this launch's own out_split, rewritten below by the same lane)
+    const uint8_t *row = p.residual_split + (long long)orow * (c_out * 4) + (c0 >> 4) * 64 + (c0 & 15) * 2;
+#pragma unroll
+    for (int j = 0; j < NC / 8; ++j) {
+      const uint4 h = *reinterpret_cast<const uint4 *>(row + 16 * j);
+      const uint4 l = *reinterpret_cast<const uint4 *>(row + 32 + 16 * j);
+      const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        y[8 * j + 2 * e] += __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
+        y[8 * j + 2 * e + 1] += __uint_as_float(hw[e] & 0xffff0000u) + __uint_as_float(lw[e] & 0xffff0000u);
+      }
     }
   }
   if (p.relu) {
@@ -690,10 +706,24 @@ static int env_int(const char *name, int dflt) {
 }
 
 // features_split: split image with c_in (multiple of 16, <= 128) channels per row.
+int spconv_v6_forward_ex(const void *features_split, const void *packed, const int32_t *nbr, long long nbr_stride,
+                         int n_in, int n_out, const int32_t *n_out_dev, int c_in, int c_out, int kvol,
+                         const float *scale, const float *shift, const float *residual, const void *residual_split,
+                         int relu, float *out, void *out_split, cudaStream_t st);
 int spconv_v6_forward(const void *features_split, const void *packed, const int32_t *nbr, long long nbr_stride,
                       int n_in, int n_out, const int32_t *n_out_dev, int c_in, int c_out, int kvol,
                       const float *scale, const float *shift, const float *residual, int relu, float *out,
                       void *out_split, cudaStream_t st) {
+  return spconv_v6_forward_ex(features_split, packed, nbr, nbr_stride, n_in, n_out, n_out_dev, c_in, c_out, kvol, scale,
+                              shift, residual, nullptr, relu, out, out_split, st);
+}
+// residual_split: the residual rows as a split image instead of fp32 rows (at most one of the two)
+int spconv_v6_forward_ex(const void *features_split, const void *packed, const int32_t *nbr, long long nbr_stride,
+                         int n_in, int n_out, const int32_t *n_out_dev, int c_in, int c_out, int kvol,
+                         const float *scale, const float *shift, const float *residual, const void *residual_split,
+                         int relu, float *out, void *out_split, cudaStream_t st) {
+  BEVB200_REQUIRE(!(residual && residual_split), "residual given twice");
+  BEVB200_REQUIRE(residual_split == nullptr || (uintptr_t)residual_split % 16 == 0, "residual image must be 16-byte aligned");
   BEVB200_REQUIRE(c_in == spconv_v6_cin_eff(c_in) && spconv_v6_shape_ok(c_in, c_out, kvol), "shape has no tensor-core form");
   BEVB200_REQUIRE(features_split && packed && nbr, "null argument");
   BEVB200_REQUIRE((uintptr_t)features_split % 16 == 0 && (out == nullptr || (uintptr_t)out % 16 == 0) &&
@@ -709,6 +739,7 @@ int spconv_v6_forward(const void *features_split, const void *packed, const int3
   p.nbr_stride = nbr_stride;
   p.n_out_dev = n_out_dev;
   p.scale = scale; p.shift = shift; p.residual = residual;
+  p.residual_split = (const uint8_t *)residual_split;
   p.out = out;
   p.out_split = (uint8_t *)out_split;
   p.n_in = n_in; p.n_out = n_out; p.c_in = c_in; p.c_out = c_out; p.kvol = kvol; p.relu = relu;
