@@ -210,6 +210,31 @@ def test_plan_full_size_c2_properties(cuda):
     assert float(gflat[dropped].abs().sum()) == 0.0
 
 
+def test_plan_full_size_c2_vs_reference_cuda_kernel(cuda):
+    """BASELINE config C2 against the reference's OWN CUDA kernel (compiled unmodified into oracle/_ref): the reference
+    path materialises x[perm] (592 MB) and runs bev_pool_forward on the sorted rows with the interval tables; the plan
+    path pools the unsorted volume through perm.  Same cells, same rows per cell in the same order -> <= 1e-4 (in fact
+    equal up to the summation tree of the wide intervals)."""
+    ref = ref_module("bev_pool_ext_ref")
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    from bevfusion_b200 import synthetic as S
+    from bevfusion_b200.bev_pool import BEVPoolPlan
+    geom, cfg = S.camera_geometry("C2", device=cuda)
+    plan = BEVPoolPlan(geom, cfg["xbound"], cfg["ybound"], cfg["zbound"])
+    t = plan.tables
+    x = S.lifted_features("C2", device=cuda, seed=1)
+    out = plan.pool(x)                                               # [1, 1, 360, 360, 80]
+    xs = x.reshape(-1, 80)[t.perm[:t.n_kept].long()].contiguous()    # what bev_pool.py:94 hands the kernel
+    torch.cuda.synchronize()
+    ref_out = ref.bev_pool_forward(xs, t.geom.contiguous(), t.lengths.contiguous(), t.starts.contiguous(), 1, 1, 360, 360)
+    torch.cuda.synchronize()
+    assert tuple(ref_out.shape) == tuple(out.shape)
+    err = (out.double() - ref_out.double()).abs().max() / ref_out.double().abs().max()
+    assert float(err) <= 1e-4
+    assert bool(((out != 0) == (ref_out != 0)).all())
+
+
 @pytest.mark.parametrize("cfg_name", ["tiny", "C2"])
 def test_fused_lift_pool(cuda, cfg_name):
     """fused LSS lift + pool == pool(depth (x) ctx) without the materialised volume."""
