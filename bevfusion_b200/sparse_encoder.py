@@ -11,9 +11,6 @@ from .sparse_block import SparseBasicBlock, bn_scale_shift, make_sparse_convmodu
 from .spconv import ops as sp_ops
 
 
-_SIDE_STREAMS = {}   # device -> stream the rulebooks are built on (fused eval path)
-
-
 class SparseEncoder(nn.Module):
     def __init__(self, in_channels, sparse_shape, order=("conv", "norm", "act"),
                  norm_cfg=dict(type="BN1d", eps=1e-3, momentum=0.01), base_channels=16,
@@ -123,9 +120,10 @@ class SparseEncoder(nn.Module):
             # rulebooks on a side stream (see SparseConvolution._rulebook): their kernels and the
             # host waits for the strided convs' output counts hide behind the queued convolutions
             dev = x.features.device
-            side = _SIDE_STREAMS.get(dev)
+            streams = self.__dict__.setdefault("_rulebook_streams", {})   # per module, not a package global
+            side = streams.get(dev)
             if side is None:
-                side = _SIDE_STREAMS[dev] = torch.cuda.Stream(device=dev)
+                side = streams[dev] = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))    # the voxel coordinates are ready
             x.indice_dict["__rulebook_stream__"] = side
             if self.rulebook_lookahead:
