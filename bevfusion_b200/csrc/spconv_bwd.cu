@@ -20,6 +20,14 @@ int spconv_forward_simt(const float *features, const float *weight, const int32_
                         const float *shift, const float *residual, int relu, float *out,
                         cudaStream_t st);
 bool spconv_wgrad_tc_ok(int c_in, int c_out, int kvol);
+const void *spconv_wgrad_tc_grad_image(const void *workspace, int n_in, int c_in);
+bool spconv_tc_runs_on_split_images(int c_in, int c_out, int kvol, int precision);
+size_t spconv_v6_packed_bytes(int c_in, int c_out, int kvol);
+int spconv_v6_pack_weights(const float *weight, int c_in, int c_out, int kvol, void *packed, cudaStream_t st);
+int spconv_v6_forward(const void *features_split, const void *packed, const int32_t *nbr, long long nbr_stride,
+                      int n_in, int n_out, const int32_t *n_out_dev, int c_in, int c_out, int kvol,
+                      const float *scale, const float *shift, const float *residual, int relu, float *out,
+                      void *out_split, cudaStream_t st);
 size_t spconv_wgrad_tc_workspace_bytes(int n_in, int n_out, int c_in, int c_out, int kvol);
 int spconv_wgrad_tc(const float *features, const float *out_grad, const int32_t *nbr, int n_in, int n_out,
                     int c_in, int c_out, int kvol, float *weight_grad, void *workspace, cudaStream_t st);
@@ -211,7 +219,8 @@ size_t bevb200_spconv_backward_workspace_bytes(int n_in, int n_out, int c_in, in
   const size_t chunks = ((size_t)n_out + kWgChunk - 1) / kWgChunk;
   const size_t simt = w * (chunks ? chunks : 1);          // one partial dW per chunk of output rows
   const size_t tc = spconv_wgrad_tc_workspace_bytes(n_in, n_out, c_in, c_out, kernel_volume);   // split images + partials
-  return w + (simt > tc ? simt : tc);                     // transposed weights + the larger of the two
+  const size_t pk = align_up(spconv_v6_packed_bytes(c_out, c_in, kernel_volume));   // W^T image of the input gradient
+  return w + (simt > tc ? simt : tc) + pk;                // transposed weights + the larger of the two + that image
 }
 
 int bevb200_spconv_backward(const float *features, const float *weight, const float *out_grad,
@@ -241,6 +250,22 @@ int bevb200_spconv_backward(const float *features, const float *weight, const fl
   BEVB200_LAUNCH(weight_transpose_kernel, grid_for((long long)kernel_volume * c_in * c_out, 256), 256, 0,
                  st, weight, kernel_volume, c_in, c_out, wt);
   int rc;
+  const bool tc_wgrad = (precision == BEVB200_PREC_BF16X3 || precision == BEVB200_PREC_TF32) &&
+                        spconv_wgrad_tc_ok(c_in, c_out, kernel_volume) && (uintptr_t)features % 16 == 0 &&
+                        (uintptr_t)out_grad % 16 == 0;
+  char *tc_ws = (char *)workspace + align_up(wbytes);
+  // One split of out_grad serves both gradients when the filter gradient's out-grad image is the generation-6 row
+  // image (c_out = 32 / 64 / 128) and the input gradient runs on generation 6: dW first, then dIn gathers from it.
+  if (tc_wgrad && (c_out == 32 || c_out == 64 || c_out == 128) &&
+      spconv_tc_runs_on_split_images(c_out, c_in, kernel_volume, precision) && (uintptr_t)input_grad % 16 == 0) {
+    rc = spconv_wgrad_tc(features, out_grad, nbr, n_in, n_out, c_in, c_out, kernel_volume, weight_grad, tc_ws, st);
+    if (rc) return rc;
+    void *packed = tc_ws + spconv_wgrad_tc_workspace_bytes(n_in, n_out, c_in, c_out, kernel_volume);
+    rc = spconv_v6_pack_weights(wt, c_out, c_in, kernel_volume, packed, st);
+    if (rc) return rc;
+    return spconv_v6_forward(spconv_wgrad_tc_grad_image(tc_ws, n_in, c_in), packed, nbr_t, n_in, n_out, n_in, nullptr, c_out,
+                             c_in, kernel_volume, nullptr, nullptr, nullptr, 0, input_grad, nullptr, st);
+  }
   if (precision == BEVB200_PREC_FP32)
     rc = spconv_forward_simt(out_grad, wt, nbr_t, n_out, n_in, c_out, c_in, kernel_volume, nullptr,
                              nullptr, nullptr, 0, input_grad, st);
@@ -249,10 +274,8 @@ int bevb200_spconv_backward(const float *features, const float *weight, const fl
                            nullptr, nullptr, 0, precision, input_grad, st);
   if (rc) return rc;
   // dW on the tensor cores (spconv_wgrad_tc.cu) for the tensor-core precisions and channel counts 32 / 64 / 128 ...
-  if ((precision == BEVB200_PREC_BF16X3 || precision == BEVB200_PREC_TF32) && spconv_wgrad_tc_ok(c_in, c_out, kernel_volume) &&
-      (uintptr_t)features % 16 == 0 && (uintptr_t)out_grad % 16 == 0)
-    return spconv_wgrad_tc(features, out_grad, nbr, n_in, n_out, c_in, c_out, kernel_volume, weight_grad,
-                           (char *)workspace + align_up(wbytes), st);
+  if (tc_wgrad)
+    return spconv_wgrad_tc(features, out_grad, nbr, n_in, n_out, c_in, c_out, kernel_volume, weight_grad, tc_ws, st);
   // ... else SIMT: per-chunk partials, then an ordered reduction (no atomics)
   const int n_chunks = (n_out + kWgChunk - 1) / kWgChunk;
   float *partial = (float *)((char *)workspace + align_up(wbytes));

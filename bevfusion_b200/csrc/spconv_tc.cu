@@ -895,6 +895,10 @@ static int tc_variant(bool bf) {
 static bool use_v6(int c_in, int c_out, int kvol, int precision) {
   return precision == BEVB200_PREC_BF16X3 && tc_variant(true) == 6 && spconv_v6_shape_ok(c_in, c_out, kvol);
 }
+// for spconv_bwd.cu: does this (shape, precision) run on generation 6, i.e. on split row images?
+bool spconv_tc_runs_on_split_images(int c_in, int c_out, int kvol, int precision) {
+  return use_v6(c_in, c_out, kvol, precision);
+}
 
 // Input channels the kernel runs with: narrow inputs (conv_input: Cin = 5) are zero-padded to 8
 // (v5; 16 for the older variants), other counts to the next power of two up to 128.  0 = no

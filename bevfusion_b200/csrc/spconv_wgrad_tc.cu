@@ -422,6 +422,12 @@ static WgtPlan wgt_plan(int n_out, int c_in, int c_out, int kvol) {
   return w;
 }
 
+// where spconv_wgrad_tc() leaves the split image of out_grad inside its workspace; for c_out = 32 / 64 / 128 it is the
+// generation-6 row image of out_grad, which the input gradient can gather from instead of splitting the rows again
+const void *spconv_wgrad_tc_grad_image(const void *workspace, int n_in, int c_in) {
+  return (const uint8_t *)workspace + align_up((size_t)n_in * wgt_eff(c_in) * 4);
+}
+
 size_t spconv_wgrad_tc_workspace_bytes(int n_in, int n_out, int c_in, int c_out, int kvol) {
   if (!spconv_wgrad_tc_ok(c_in, c_out, kvol) || n_in <= 0 || n_out <= 0) return 0;
   const WgtPlan w = wgt_plan(n_out, c_in, c_out, kvol);
