@@ -122,6 +122,17 @@ def test_size_queries_of_the_later_entry_points():
     assert L.bevb200_depth_rasterize_workspace_bytes(0, 256, 704) == 0
     assert L.bevb200_dynamic_scatter_workspace_bytes(300000) > 300000 * (8 + 8 + 4 + 4 + 4 + 4 + 4)
     assert L.bevb200_dynamic_scatter_workspace_bytes(0) > 0
+    # sparse-conv backward workspace: transposed weights + (operand images of the tensor-core filter gradient: input rows
+    # and out-grad rows at 4 B per element, channels padded to 32 / 64 / 128, + per-chunk partial dW) + the packed W^T
+    ws = L.bevb200_spconv_backward_workspace_bytes
+    n_in, n_out = 70000, 50000
+    for c_in, c_out in ((64, 64), (16, 32), (5, 16), (128, 128)):
+        ce_in, ce_out = max(32, c_in if c_in in (64, 128) else 32), max(32, c_out if c_out in (64, 128) else 32)
+        images = n_in * ce_in * 4 + n_out * ce_out * 4
+        assert ws(n_in, n_out, c_in, c_out, 27) >= 27 * c_in * c_out * 4 + images
+        assert ws(2 * n_in, n_out, c_in, c_out, 27) >= ws(n_in, n_out, c_in, c_out, 27) + n_in * ce_in * 4   # grows with n_in
+    assert ws(1000, 1000, 48, 48, 27) > 0                                  # no tensor-core form: the SIMT partials
+    assert ws(-1, 10, 16, 16, 27) == 0 and ws(10, 10, 0, 16, 27) == 0     # bad sizes
 
 
 def test_output_view_validation():
